@@ -1,0 +1,215 @@
+/*
+ * megba_b200.h -- C-ABI of the Blackwell-native LM / Schur-PCG hot path.
+ *
+ * This is the drop-in boundary.  MegBA itself has no FFI
+ * seam: its seams are C++ virtual interfaces between static libraries that own raw
+ * device pointers.  Each entry point below replaces one of those seams and cites
+ * it (paths relative to the MegBA checkout).  INTEGRATION.md shows the binding a
+ * MegBA maintainer adds on the reference side; include/megba/ is the C++ facade
+ * that reproduces the reference's class names on top of these functions.
+ *
+ * Conventions: plain C types only; every function returns BA_OK (0) or a negative
+ * ba_status and never throws; `void*` numeric buffers are HOST arrays of the
+ * solver's dtype (double for BA_F64, float for BA_F32); one ba_solver is bound to
+ * one CUDA device and one rank (one process per GPU; several solvers in one
+ * process, one host thread each, also work); all device memory is allocated in
+ * ba_create; there is no CPU fallback -- without a CUDA device ba_create fails with
+ * BA_ERR_NO_DEVICE.
+ */
+#ifndef MEGBA_B200_H_
+#define MEGBA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEGBA_B200_ABI_VERSION 1
+
+typedef enum {
+  BA_OK = 0,
+  BA_ERR_ARG = -1,       /* bad argument / inconsistent graph                    */
+  BA_ERR_NO_DEVICE = -2, /* no usable CUDA device (the product has no CPU path)  */
+  BA_ERR_CUDA = -3,      /* a CUDA runtime call or kernel failed                 */
+  BA_ERR_NCCL = -4,      /* an NCCL call failed                                  */
+  BA_ERR_STATE = -5,     /* call sequence violated (e.g. solve before linearize) */
+  BA_ERR_ALLOC = -6
+} ba_status;
+
+typedef enum { BA_F64 = 0, BA_F32 = 1 } ba_dtype;
+/* ComputeKind{EXPLICIT, IMPLICIT}, include/common.h:21 */
+typedef enum { BA_EXPLICIT = 0, BA_IMPLICIT = 1 } ba_compute_kind;
+
+/* ProblemOption (include/common.h:44-53) restricted to what the hot path needs.
+ * deviceUsed[i] becomes one solver with device = deviceUsed[i], rank = i.         */
+typedef struct {
+  int32_t dtype;        /* ba_dtype                                              */
+  int32_t compute_kind; /* ba_compute_kind                                       */
+  int32_t device;       /* CUDA ordinal                                          */
+  int32_t rank;         /* 0 .. world_size-1                                     */
+  int32_t world_size;   /* number of GPUs = ProblemOption::deviceUsed.size()     */
+  int32_t reserved[3];
+} ba_options;
+
+/* SolverOption::SolverOptionPCG, include/common.h:27-33 */
+typedef struct {
+  int32_t max_iter;
+  int32_t reserved;
+  double tol;
+  double refuse_ratio;
+} ba_pcg_options;
+
+/* AlgoOption::AlgoOptionLM, include/common.h:35-42 */
+typedef struct {
+  int32_t max_iter;
+  int32_t reserved;
+  double initial_region;
+  double epsilon1;
+  double epsilon2;
+} ba_lm_options;
+
+/* One row per LM iteration; row 0 is the "Start with error" line
+ * (src/algo/lm_algo.cu:149-150,190-191,207).                                      */
+typedef struct {
+  double cost;      /* F = sum r^2 after this iteration (console prints F/2)     */
+  int32_t accepted; /* 1 accepted, 0 "Iter k failed", -1 stopped on step size    */
+  int32_t pcg_iters;
+  double region;
+  double dx_norm;
+  double rho;
+  double elapsed_ms; /* cumulative, like the reference's trace                   */
+} ba_lm_trace;
+
+/* Device-side timing / launch accounting since the last ba_reset_stats.
+ * ms values are CUDA-event times on the solver's stream.                          */
+typedef struct {
+  int64_t launches;          /* kernels of this library launched                 */
+  int64_t lm_iters;          /* LM iterations executed (accepted + rejected)     */
+  int64_t pcg_iters;         /* PCG iterations executed (n of schur_pcg :405)    */
+  int64_t schur_apply_calls; /* launches of the S*p edge kernel                  */
+  double schur_apply_ms;     /* summed device time of those launches (timing on) */
+  int64_t linearize_calls;
+  double linearize_ms;       /* summed device time of ba_linearize (timing on)   */
+  double pcg_loop_ms;        /* device time inside the PCG do-while bodies       */
+  double solve_ms;           /* device time of ba_solve (inverse+MakeV+PCG+SolveW)*/
+  double reserved[4];
+} ba_stats;
+
+typedef struct ba_solver ba_solver;
+
+int ba_abi_version(void);
+
+/* Host-only helper, no GPU needed.  Partition rule replacing MemoryPool::getItemNum
+ * (include/resource/memory_pool.h:48-63) + the device walk in BaseProblem::appendEdge
+ * (src/problem/base_problem.cpp:116-121): points are cut into world_size contiguous
+ * ranges balanced by edge count, so every edge of a point lives on one rank.
+ * pt_degree[nP] = observations per point; pt_begin[world_size+1] receives the cuts. */
+int ba_partition_points(int64_t nP, const int64_t *pt_degree, int32_t world_size,
+                        int64_t *pt_begin);
+
+/* BaseProblem::appendVertex/appendEdge + buildIndex (src/problem/base_problem.cpp:
+ * 82-125,183-214), EdgeVector::buildPositionContainer/allocateResource
+ * (src/edge/base_edge.cpp:224-262, src/edge/base_edge.cu:47-103) and
+ * SchurLMLinearSystem::buildIndex/allocateResourceCUDA
+ * (src/linear_system/schur_LM_linear_system.cpp:53-84, .cu:29-110).
+ * cam_idx/pt_idx: vertex numbers of each observation (any order, every rank passes
+ * the full list); obs[nE][2] in the solver dtype.                                  */
+int ba_create(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE,
+              const int32_t *cam_idx, const int32_t *pt_idx, const void *obs,
+              ba_solver **out);
+void ba_destroy(ba_solver *s);
+const char *ba_last_error(const ba_solver *s);
+
+/* HandleManager NCCL set-up (src/resource/handle_manager.cpp:17-21), one process per
+ * GPU: rank 0 calls ba_comm_unique_id, ships the 128 bytes to every rank by any
+ * means, every rank calls ba_comm_init.  Not needed for world_size == 1.           */
+int ba_comm_unique_id(void *id128);
+int ba_comm_init(ba_solver *s, const void *id128);
+
+/* BaseProblem::setAbsolutePosition (H2D of x, src/problem/base_problem.cpp:217-247)
+ * and writeBack (:250-272).  cam[nC][9], pt[nP][3].                                */
+int ba_set_params(ba_solver *s, const void *cam, const void *pt);
+int ba_get_params(ba_solver *s, void *cam, void *pt);
+
+/* Optional per-edge 2x2 information matrices, info[nE][4] row-major
+ * (BaseEdge::setInformation; JMulInfo/makeHSchurWithInfo,
+ * src/edge/build_linear_system.cu:149-239).  NULL restores identity.              */
+int ba_set_information(ba_solver *s, const void *info);
+
+/* HP1.  EdgeVector::forward + buildLinearSystem (src/edge/base_edge.cpp:160-163,
+ * src/geo/analytical_derivatives.cu:162-322, src/edge/build_linear_system.cu:243-423
+ * or build_implicit_linear_system.cu:208-322) + computeResidualNorm
+ * (src/algo/lm_algo.cu:26-51): fills Hpp, Hll, Hpl(=W) or J, g at the current
+ * parameters; *cost = sum r^2 over all ranks.                                      */
+int ba_linearize(ba_solver *s, double *cost);
+
+/* LMLinearSystem::processDiag (src/linear_system/schur_LM_linear_system.cu:162-185).
+ * The undamped blocks are kept; damping (1 + 1/region) is applied when the blocks
+ * are consumed, so recover != 0 ("recoverDiag") needs no saved diagonal.           */
+int ba_process_diag(ba_solver *s, double region, int recover);
+
+/* HP2.  BaseLinearSystem::solve -> SchurPCGSolver::solve /
+ * ImplicitSchurPCGSolver::solve (src/solver/schur_pcg_solver.cu:599-679,
+ * src/solver/implicit_schur_pcg_solver.cu:661-720): block inverses, Schur RHS,
+ * warm-started PCG, back-substitution.  Result in the solver's deltaX.            */
+int ba_solve(ba_solver *s, const ba_pcg_options *opt, int32_t *iters, int32_t *done);
+
+/* ||deltaX||_2 and ||x||_2 (l2NormPow2, src/algo/lm_algo.cu:54-58,172-175).       */
+int ba_step_norms(ba_solver *s, double *dx_norm, double *x_norm);
+
+/* EdgeVector::update + forward at the trial point + computeResidualNorm +
+ * computeRhoDenominator (src/edge/update.cu:45-62, src/algo/lm_algo.cu:61-126,
+ * 180-185): *cost_new = sum r(x+dx)^2, *model_sq = sum (J dx + r)^2 (caller
+ * subtracts F).  x itself is not modified.                                        */
+int ba_eval_trial(ba_solver *s, double *cost_new, double *model_sq);
+
+/* Accept: applyUpdate (x += dx, schur_LM_linear_system.cu:212-218), backup of
+ * deltaX (:188-197); the caller then re-linearises.  *g_inf = ||g||_inf of the
+ * CURRENT g (call after ba_linearize; linfNorm, lm_algo.cu:129-136,203-205).
+ * Reject: rollback of deltaX (:200-209).                                          */
+int ba_accept_step(ba_solver *s);
+int ba_reject_step(ba_solver *s);
+int ba_grad_inf_norm(ba_solver *s, double *g_inf);
+
+/* LMAlgo::solveCUDA (src/algo/lm_algo.cu:139-223) on top of the calls above.
+ * trace may be NULL; at most trace_cap rows are written, *n_trace = rows produced.
+ * verbose != 0 prints the reference's console trace.                               */
+int ba_lm_solve(ba_solver *s, const ba_lm_options *lm, const ba_pcg_options *pcg,
+                ba_lm_trace *trace, int32_t trace_cap, int32_t *n_trace, int32_t verbose);
+
+/* Parity / inspection access.  Buffers are host arrays in the solver dtype, indexed
+ * in the CALLER's edge and vertex numbering, reference layouts:
+ *   BA_BUF_HPP [nC][9][9]   equationContainers.csrVal[2]  (row-major blocks)
+ *   BA_BUF_HLL [nP][3][3]   csrVal[3]
+ *   BA_BUF_W   [nE][9][3]   csrVal[0] = Hpl block of each observation (explicit)
+ *   BA_BUF_J   [nE][2][12]  JVD grad slabs (implicit mode, or via ba_eval_edges)
+ *   BA_BUF_G   [9nC+3nP]    g
+ *   BA_BUF_DX  [9nC+3nP]    deltaXPtr
+ * On world_size > 1 vertex/edge rows owned by other ranks read as zero for HLL/W/J
+ * and the point parts of G/DX.                                                     */
+typedef enum { BA_BUF_HPP = 0, BA_BUF_HLL = 1, BA_BUF_W = 2, BA_BUF_J = 3, BA_BUF_G = 4, BA_BUF_DX = 5 } ba_buffer;
+int ba_read(ba_solver *s, int32_t which, void *host_out);
+int ba_write_dx(ba_solver *s, const void *dx); /* warm start for ba_solve */
+
+/* Residuals r[nE][2] and (if J != NULL) Jacobians J[nE][2][12] at the current
+ * parameters (analytical_derivatives.cu:162-285), caller's edge order.            */
+int ba_eval_edges(ba_solver *s, void *r, void *J);
+
+/* q = S p for a host vector p[9nC] with the current damped blocks:
+ * one operator application of the PCG loop (schur_pcg_solver.cu:315-366).          */
+int ba_schur_apply(ba_solver *s, const void *p, void *q);
+
+int ba_set_timing(ba_solver *s, int32_t on);
+int ba_reset_stats(ba_solver *s);
+int ba_get_stats(ba_solver *s, ba_stats *out);
+/* Algorithmic bytes of one S*p edge-kernel launch and one linearisation on THIS
+ * rank (SURVEY.md section 8d formulas).                             */
+int ba_algorithmic_bytes(ba_solver *s, double *schur_apply_bytes, double *linearize_bytes);
+/* The CUDA stream (cudaStream_t) all of this solver's work is enqueued on.         */
+void *ba_stream(ba_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEGBA_B200_H_ */
