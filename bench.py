@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s and PCG iterations/s on the Venice-1778-shaped problem (fp64).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host threads)
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic BAL problem
+with Venice's exact shape (1778 cameras, 993923 points, 5001946 observations; no BAL file and no network
+on the box), fp64, explicit Schur, fixed-work mode of SURVEY.md section 8d: every LM iteration runs exactly
+`--pcg-iters` (default 50) PCG iterations (tol 0, refuse ratio inf), LM stop tests disabled.
+
+A *step* is one Levenberg-Marquardt iteration (lm_algo.cu:163-221): damping, Schur-PCG solve, step norms,
+trial cost + gain ratio, and -- when accepted -- re-linearisation.
+  value : K iterations inside ONE ba_lm_solve call, everything resident in HBM (device-event timed).
+  e2e   : K calls of the reference-facing flow problem.solve() with max_iter = 1 on HOST buffers:
+          H2D of the parameter vector (pinned), initial linearisation, one LM iteration, D2H of the
+          result (pinned) -- BaseProblem::solve = buildIndex/H2D -> algo.solve -> writeBack.
+Multi-GPU: one process per GPU; points (hence observations) are sharded, cameras replicated; per PCG
+iteration one NCCL allreduce of the 9*nC camera vector.  Total work is fixed => "strong" scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "venice-1778"
+LM_REGION = 1e4  # README's --tau for Venice (README.md:58)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pcg-iters", type=int, default=50)
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--implicit", action="store_true")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_lm_iteration(P, pcg_iters, implicit, dtype):
+    """One LM iteration (incl. the start linearisation) of the CPU oracle; returns seconds, pcg iters, threads."""
+    from oracle.oracle import Oracle
+    O = Oracle(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype)
+    x0 = P.x(dtype)
+    t0 = time.perf_counter()
+    _, _, tr = O.lm_solve(x0, implicit=implicit, lm_max_iter=1, initial_region=LM_REGION, eps1=0.0, eps2=0.0,
+                          pcg_max_iter=pcg_iters, pcg_tol=0.0, pcg_refuse=1e300)
+    dt = time.perf_counter() - t0
+    return dt, sum(t["pcg_iters"] for t in tr), O.num_threads(), tr
+
+
+def run_reference(args, P, dtype):
+    """CPU arm: the reference has no CPU execution path (every Device::CPU branch throws) and cannot be
+    built here (Eigen/gflags absent), so this times the oracle port of its algorithm on all host threads."""
+    sample_pcg = args.pcg_iters
+    times, pcg_total = [], 0
+    threads = 0
+    # bound the whole run to a few minutes: shrink the per-step PCG count if a step is too slow
+    dt, npcg, threads, _ = oracle_lm_iteration(P, sample_pcg, args.implicit, dtype)  # warm-up 1 (also calibrates)
+    budget = 240.0
+    total_steps = args.steps + max(args.warmup - 1, 0)
+    scale = 1.0
+    if dt * total_steps > budget and sample_pcg > 5:
+        per_pcg = dt / (sample_pcg + 12.0)  # linearisations etc. cost roughly a dozen PCG iterations
+        sample_pcg = max(5, int((budget / total_steps) / per_pcg - 12))
+        scale = None
+    for _ in range(max(args.warmup - 1, 0)):
+        oracle_lm_iteration(P, sample_pcg, args.implicit, dtype)
+    for _ in range(args.steps):
+        dt, npcg, threads, _ = oracle_lm_iteration(P, sample_pcg, args.implicit, dtype)
+        times.append(dt)
+        pcg_total += npcg
+    t_step = sum(times) / len(times)
+    if scale is None:
+        # extrapolate the sampled step to the full --pcg-iters step (PCG part scales linearly)
+        per_pcg = t_step / (sample_pcg + 12.0)
+        t_step = per_pcg * (args.pcg_iters + 12.0)
+    value = 1.0 / t_step
+    sample = (f"{args.steps} x [1 LM iteration = 2 linearisations + {sample_pcg} PCG iterations] of the same "
+              f"{P.label} problem" + ("" if scale else f", extrapolated to {args.pcg_iters} PCG iterations/step"))
+    line = {
+        "impl": "reference", "metric": "lm_iters_per_sec", "value": value, "unit": "LM it/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": bench_config(args, P),
+        "pcg_iters_per_sec": None,
+        "cpu_baseline": {"value": value, "unit": "LM it/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "LM it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(args, P):
+    return {"workload": f"{P.label} ({P.nC} cameras, {P.nP} points, {P.nE} observations)",
+            "compute_kind": "implicit" if args.implicit else "explicit",
+            "lm": {"tau": LM_REGION, "epsilon1": 0, "epsilon2": 0},
+            "pcg": {"iters_per_lm_iter": args.pcg_iters, "tol": 0, "refuse_ratio": "inf"},
+            "parallelism": f"point-sharded edges x{args.gpus}, cameras replicated",
+            "l2": "working set per PCG iteration (>1 GB) exceeds the 126 MB L2; no explicit flush"}
+
+
+def run_ours(args, P, dtype):
+    import torch
+    import torch.distributed as dist
+
+    from megba_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={ws}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    if ws > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", local))
+
+    S = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype=dtype, implicit=args.implicit, device=local,
+                    rank=rank, world_size=ws)
+    if ws > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.Solver.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        S.comm_init(bytes(uid.cpu().numpy().tobytes()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if ws == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cam_in = torch.from_numpy(P.cam.astype(dtype)).pin_memory()
+    pt_in = torch.from_numpy(P.pt.astype(dtype)).pin_memory()
+    cam_out = torch.empty_like(cam_in).pin_memory()
+    pt_out = torch.empty_like(pt_in).pin_memory()
+    stream = torch.cuda.ExternalStream(S.stream())
+    kw = dict(initial_region=LM_REGION, eps1=0.0, eps2=0.0, pcg_max_iter=args.pcg_iters, pcg_tol=0.0,
+              pcg_refuse=1e300)
+
+    # ---------------- resident arm: K iterations in one ba_lm_solve call
+    S.set_params_ptr(cam_in.data_ptr(), pt_in.data_ptr())
+    S.lm_solve(lm_max_iter=max(args.warmup, 3), **kw)  # warm-up (>= 3 iterations)
+    S.set_params_ptr(cam_in.data_ptr(), pt_in.data_ptr())
+    S.set_timing(True)
+    S.reset_stats()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    trace = S.lm_solve(lm_max_iter=args.steps, **kw)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    st = S.stats()
+    S.set_timing(False)
+    n_iter = len(trace) - 1
+    assert n_iter == args.steps, (n_iter, args.steps)
+    ms_total = max_over_ranks(dev_ms)
+    wall = max_over_ranks(wall)
+    lm_rate = args.steps / (ms_total * 1e-3)
+    pcg_rate = st["pcg_iters"] / (max_over_ranks(st["pcg_loop_ms"]) * 1e-3)
+    a_pcg, a_lin = S.algorithmic_bytes()
+    peak, peak_src = peaks()
+    k_ms = max_over_ranks(st["schur_apply_ms"] / max(st["schur_apply_calls"], 1))
+    achieved = a_pcg / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("k_schur_edge_full_f64" if dtype == np.float64 else "k_schur_edge_full_f32")
+    roofline = {"bound": "hbm", "kernel": "k_schur_edge<FULL> (S*p edge pass of one PCG iteration)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": a_pcg,
+                "avg_launch_ms": k_ms, "launches_timed": st["schur_apply_calls"],
+                "linearize": {"algorithmic_bytes": a_lin,
+                              "avg_ms": st["linearize_ms"] / max(st["linearize_calls"], 1),
+                              "achieved": a_lin / (st["linearize_ms"] / max(st["linearize_calls"], 1) * 1e-3) / 1e9}}
+    launches = st["launches"]
+
+    # ---------------- end-to-end arm: K solve() calls on host buffers
+    def e2e_step():
+        S.set_params_ptr(cam_in.data_ptr(), pt_in.data_ptr())
+        tr = S.lm_solve(lm_max_iter=1, **kw)
+        S.get_params_ptr(cam_out.data_ptr(), pt_out.data_ptr())
+        return tr[-1]["cost"]
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cost = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    itemsize = np.dtype(dtype).itemsize
+    bytes_x = (9 * P.nC + 3 * P.nP) * itemsize
+    e2e = {"value": args.steps / e2e_s, "unit": "LM it/s", "h2d_bytes_per_step": bytes_x,
+           "d2h_bytes_per_step": bytes_x + 8, "ms_per_step": 1e3 * e2e_s / args.steps,
+           "what": "set_params(H2D) + ba_lm_solve(max_iter=1) + get_params(D2H) per step", "final_cost": cost}
+
+    cpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        dt, npcg, threads, _ = oracle_lm_iteration(P, args.pcg_iters, args.implicit, dtype)
+        dt2, npcg, threads, _ = oracle_lm_iteration(P, args.pcg_iters, args.implicit, dtype)
+        dt = min(dt, dt2)
+        cpu = {"value": 1.0 / dt, "unit": "LM it/s", "cores": threads, "kind": "port",
+               "pcg_iters_per_sec": None,
+               "sample": f"best of 2 x [1 LM iteration = 2 linearisations + {npcg} PCG iterations] of the same "
+                         f"problem, oracle port (OpenMP, {threads} threads)"}
+
+    if rank == 0:
+        line = {
+            "metric": "lm_iters_per_sec", "value": lm_rate, "unit": "LM it/s", "n_gpus": ws, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": bench_config(args, P),
+            "pcg_iters_per_sec": pcg_rate, "pcg_iters_timed": st["pcg_iters"],
+            "accepted_steps": sum(1 for t in trace[1:] if t["accepted"] == 1),
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "final_cost": trace[-1]["cost"], "start_cost": trace[0]["cost"],
+        }
+        print(json.dumps(line), flush=True)
+    S.close()
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    from megba_b200.synthetic import make_named
+    P = make_named(args.workload)
+    if args.impl == "reference":
+        run_reference(args, P, dtype)
+    else:
+        run_ours(args, P, dtype)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,270 @@
+"""ctypes binding of the C-ABI in include/megba_b200.h (test / benchmark harness).
+
+This module only forwards to libmegba_b200.so.  There is deliberately no Python or
+CPU implementation behind it: if the library is missing or no CUDA device is present
+the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmegba_b200.so")
+
+BA_F64, BA_F32 = 0, 1
+BA_EXPLICIT, BA_IMPLICIT = 0, 1
+BUF_HPP, BUF_HLL, BUF_W, BUF_J, BUF_G, BUF_DX = range(6)
+
+# every symbol include/megba_b200.h declares (tests check the export list against the header)
+SYMBOLS = [
+    "ba_abi_version", "ba_partition_points", "ba_create", "ba_destroy", "ba_last_error",
+    "ba_comm_unique_id", "ba_comm_init", "ba_set_params", "ba_get_params", "ba_set_information",
+    "ba_linearize", "ba_process_diag", "ba_solve", "ba_step_norms", "ba_eval_trial",
+    "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
+    "ba_eval_edges", "ba_schur_apply", "ba_set_timing", "ba_reset_stats", "ba_get_stats",
+    "ba_algorithmic_bytes", "ba_stream",
+]
+
+
+class Options(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("compute_kind", C.c_int32), ("device", C.c_int32),
+                ("rank", C.c_int32), ("world_size", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class PcgOptions(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("reserved", C.c_int32), ("tol", C.c_double),
+                ("refuse_ratio", C.c_double)]
+
+
+class LmOptions(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("reserved", C.c_int32), ("initial_region", C.c_double),
+                ("epsilon1", C.c_double), ("epsilon2", C.c_double)]
+
+
+class LmTrace(C.Structure):
+    _fields_ = [("cost", C.c_double), ("accepted", C.c_int32), ("pcg_iters", C.c_int32),
+                ("region", C.c_double), ("dx_norm", C.c_double), ("rho", C.c_double),
+                ("elapsed_ms", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("launches", C.c_int64), ("lm_iters", C.c_int64), ("pcg_iters", C.c_int64),
+                ("schur_apply_calls", C.c_int64), ("schur_apply_ms", C.c_double),
+                ("linearize_calls", C.c_int64), ("linearize_ms", C.c_double),
+                ("pcg_loop_ms", C.c_double), ("solve_ms", C.c_double), ("reserved", C.c_double * 4)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_lib = None
+
+
+def load():
+    """dlopen the product library; raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(megba_b200 has no CPU or pure-Python fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.ba_last_error.restype = C.c_char_p
+        L.ba_last_error.argtypes = [C.c_void_p]
+        L.ba_stream.restype = C.c_void_p
+        L.ba_stream.argtypes = [C.c_void_p]
+        L.ba_destroy.restype = None
+        L.ba_destroy.argtypes = [C.c_void_p]
+        L.ba_create.argtypes = [C.POINTER(Options), C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ba_partition_points.argtypes = [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
+        for name in ("ba_comm_init", "ba_set_params", "ba_get_params", "ba_set_information", "ba_linearize",
+                     "ba_solve", "ba_step_norms", "ba_eval_trial", "ba_accept_step", "ba_reject_step",
+                     "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx", "ba_eval_edges",
+                     "ba_schur_apply", "ba_set_timing", "ba_reset_stats", "ba_get_stats",
+                     "ba_algorithmic_bytes"):
+            getattr(L, name).restype = C.c_int
+        L.ba_process_diag.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.ba_process_diag.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def partition_points(pt_degree: np.ndarray, world_size: int) -> np.ndarray:
+    deg = np.ascontiguousarray(pt_degree, dtype=np.int64)
+    out = np.zeros(world_size + 1, dtype=np.int64)
+    rc = load().ba_partition_points(len(deg), deg.ctypes.data_as(C.c_void_p), world_size,
+                                    out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"ba_partition_points failed: {rc}")
+    return out
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Solver:
+    """Thin owner of one ba_solver handle; method names follow the C-ABI."""
+
+    def __init__(self, nC, nP, cam_idx, pt_idx, obs, dtype=np.float64, implicit=False, device=0, rank=0,
+                 world_size=1):
+        self.L = load()
+        self.dtype = np.dtype(dtype)
+        self.nC, self.nP, self.nE = int(nC), int(nP), int(len(cam_idx))
+        self.implicit = bool(implicit)
+        opt = Options(BA_F64 if self.dtype == np.float64 else BA_F32, BA_IMPLICIT if implicit else BA_EXPLICIT,
+                      device, rank, world_size)
+        cam_idx = np.ascontiguousarray(cam_idx, dtype=np.int32)
+        pt_idx = np.ascontiguousarray(pt_idx, dtype=np.int32)
+        obs = np.ascontiguousarray(obs, dtype=self.dtype)
+        self.h = C.c_void_p()
+        rc = self.L.ba_create(C.byref(opt), self.nC, self.nP, self.nE, _p(cam_idx), _p(pt_idx), _p(obs),
+                              C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError(f"ba_create failed ({rc}): {self.L.ba_last_error(None).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.ba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.L.ba_last_error(self.h).decode()}")
+
+    def _a(self, a):
+        return np.ascontiguousarray(a, dtype=self.dtype)
+
+    # -- communicator
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load().ba_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"ba_comm_unique_id failed: {rc}")
+        return buf.raw
+
+    def comm_init(self, uid: bytes):
+        self._chk(self.L.ba_comm_init(self.h, C.c_char_p(uid)), "ba_comm_init")
+
+    # -- parameters
+    def set_params(self, cam, pt):
+        cam, pt = self._a(cam), self._a(pt)
+        self._chk(self.L.ba_set_params(self.h, _p(cam), _p(pt)), "ba_set_params")
+
+    def set_params_ptr(self, cam_ptr: int, pt_ptr: int):
+        self._chk(self.L.ba_set_params(self.h, C.c_void_p(cam_ptr), C.c_void_p(pt_ptr)), "ba_set_params")
+
+    def get_params_ptr(self, cam_ptr: int, pt_ptr: int):
+        self._chk(self.L.ba_get_params(self.h, C.c_void_p(cam_ptr), C.c_void_p(pt_ptr)), "ba_get_params")
+
+    def get_params(self):
+        cam = np.empty((self.nC, 9), self.dtype)
+        pt = np.empty((self.nP, 3), self.dtype)
+        self._chk(self.L.ba_get_params(self.h, _p(cam), _p(pt)), "ba_get_params")
+        return cam, pt
+
+    def set_information(self, info):
+        info = None if info is None else self._a(info)
+        self._chk(self.L.ba_set_information(self.h, _p(info)), "ba_set_information")
+
+    # -- hot path
+    def linearize(self) -> float:
+        c = C.c_double()
+        self._chk(self.L.ba_linearize(self.h, C.byref(c)), "ba_linearize")
+        return c.value
+
+    def process_diag(self, region: float, recover: bool = False):
+        self._chk(self.L.ba_process_diag(self.h, C.c_double(region), int(recover)), "ba_process_diag")
+
+    def solve(self, max_iter=100, tol=1e-1, refuse_ratio=1.0):
+        o = PcgOptions(max_iter, 0, tol, refuse_ratio)
+        it, done = C.c_int32(), C.c_int32()
+        self._chk(self.L.ba_solve(self.h, C.byref(o), C.byref(it), C.byref(done)), "ba_solve")
+        return it.value, bool(done.value)
+
+    def step_norms(self):
+        a, b = C.c_double(), C.c_double()
+        self._chk(self.L.ba_step_norms(self.h, C.byref(a), C.byref(b)), "ba_step_norms")
+        return a.value, b.value
+
+    def eval_trial(self):
+        a, b = C.c_double(), C.c_double()
+        self._chk(self.L.ba_eval_trial(self.h, C.byref(a), C.byref(b)), "ba_eval_trial")
+        return a.value, b.value
+
+    def accept_step(self):
+        self._chk(self.L.ba_accept_step(self.h), "ba_accept_step")
+
+    def reject_step(self):
+        self._chk(self.L.ba_reject_step(self.h), "ba_reject_step")
+
+    def grad_inf_norm(self) -> float:
+        g = C.c_double()
+        self._chk(self.L.ba_grad_inf_norm(self.h, C.byref(g)), "ba_grad_inf_norm")
+        return g.value
+
+    def lm_solve(self, lm_max_iter=20, initial_region=1e3, eps1=1.0, eps2=1e-10, pcg_max_iter=100, pcg_tol=1e-1,
+                 pcg_refuse=1.0, verbose=False):
+        lm = LmOptions(lm_max_iter, 0, initial_region, eps1, eps2)
+        pcg = PcgOptions(pcg_max_iter, 0, pcg_tol, pcg_refuse)
+        cap = lm_max_iter + 2
+        tr = (LmTrace * cap)()
+        nt = C.c_int32()
+        self._chk(self.L.ba_lm_solve(self.h, C.byref(lm), C.byref(pcg), tr, cap, C.byref(nt), int(verbose)),
+                  "ba_lm_solve")
+        return [dict(cost=t.cost, accepted=t.accepted, pcg_iters=t.pcg_iters, region=t.region,
+                     dx_norm=t.dx_norm, rho=t.rho, elapsed_ms=t.elapsed_ms) for t in tr[:min(nt.value, cap)]]
+
+    # -- inspection
+    def read(self, which):
+        shape = {BUF_HPP: (self.nC, 9, 9), BUF_HLL: (self.nP, 3, 3), BUF_W: (self.nE, 9, 3),
+                 BUF_J: (self.nE, 2, 12), BUF_G: (9 * self.nC + 3 * self.nP,),
+                 BUF_DX: (9 * self.nC + 3 * self.nP,)}[which]
+        out = np.empty(shape, self.dtype)
+        self._chk(self.L.ba_read(self.h, which, _p(out)), "ba_read")
+        return out
+
+    def write_dx(self, dx):
+        dx = self._a(dx)
+        self._chk(self.L.ba_write_dx(self.h, _p(dx)), "ba_write_dx")
+
+    def eval_edges(self, jac=True):
+        r = np.empty((self.nE, 2), self.dtype)
+        J = np.empty((self.nE, 2, 12), self.dtype) if jac else None
+        self._chk(self.L.ba_eval_edges(self.h, _p(r), _p(J)), "ba_eval_edges")
+        return r, J
+
+    def schur_apply(self, p):
+        p = self._a(p)
+        q = np.empty(9 * self.nC, self.dtype)
+        self._chk(self.L.ba_schur_apply(self.h, _p(p), _p(q)), "ba_schur_apply")
+        return q
+
+    def set_timing(self, on: bool):
+        self._chk(self.L.ba_set_timing(self.h, int(on)), "ba_set_timing")
+
+    def reset_stats(self):
+        self._chk(self.L.ba_reset_stats(self.h), "ba_reset_stats")
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._chk(self.L.ba_get_stats(self.h, C.byref(s)), "ba_get_stats")
+        return s.asdict()
+
+    def algorithmic_bytes(self):
+        a, b = C.c_double(), C.c_double()
+        self._chk(self.L.ba_algorithmic_bytes(self.h, C.byref(a), C.byref(b)), "ba_algorithmic_bytes")
+        return a.value, b.value
+
+    def stream(self) -> int:
+        return int(self.L.ba_stream(self.h) or 0)

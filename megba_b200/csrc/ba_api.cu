@@ -1,0 +1,898 @@
+// ba_api.cu -- host side of the C-ABI in include/megba_b200.h: graph preprocessing
+// (point-major tiling, camera-major view, point partition), the device arena, the
+// Schur-PCG driver, the LM loop and NCCL plumbing.  No CPU compute path exists here:
+// every numeric result is produced by the kernels in ba_kernels.cu.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/megba_b200.h"
+#include "ba_internal.h"
+
+namespace ba {
+
+#define BA_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) return fail(BA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define BA_NCCL(expr)                                                                          \
+  do {                                                                                         \
+    ncclResult_t e__ = (expr);                                                                 \
+    if (e__ != ncclSuccess) return fail(BA_ERR_NCCL, "%s: %s", #expr, ncclGetErrorString(e__)); \
+  } while (0)
+#define BA_TRY(expr)              \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != BA_OK) return rc__; \
+  } while (0)
+
+template <typename T> struct NcclType;
+template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
+template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
+
+// Host-side, dtype-independent result of graph preprocessing.
+struct HostGraph {
+  int64_t nC = 0, nP = 0, nE = 0;
+  int64_t pt_begin = 0, pt_end = 0;  // this rank's points
+  int nPl = 0, nT = 0, nSlabs = 0, nChunks = 0, nEl = 0;
+  std::vector<int4> tile;
+  std::vector<int> e_cam;
+  std::vector<unsigned short> e_lp;
+  std::vector<int> pt_slot;
+  std::vector<int64_t> edge_of_slot;   // -1 for padding
+  std::vector<int32_t> slot_of_edge;   // [nE], -1 if the edge lives on another rank
+  std::vector<int4> chunk;
+  std::vector<int> cam_chunk_ptr;
+  std::vector<int> cm_pt;
+  std::vector<int> cm_slot;            // slot of each camera-major entry
+};
+
+static int partition_points(int64_t nP, const int64_t *deg, int ws, int64_t *cuts) {
+  if (nP < 0 || ws < 1 || !cuts || (nP > 0 && !deg)) return BA_ERR_ARG;
+  int64_t total = 0;
+  for (int64_t p = 0; p < nP; ++p) total += deg[p];
+  cuts[0] = 0;
+  int64_t p = 0, acc = 0;
+  for (int r = 1; r < ws; ++r) {
+    const double target = (double)total * r / ws;
+    while (p < nP && (double)acc + 0.5 * (double)deg[p] < target) acc += deg[p++];
+    cuts[r] = p;
+  }
+  cuts[ws] = nP;
+  return BA_OK;
+}
+
+static int build_host_graph(const ba_options &opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx,
+                            const int32_t *pt_idx, HostGraph &g, std::string &err) {
+  g.nC = nC; g.nP = nP; g.nE = nE;
+  if (nC <= 0 || nP <= 0 || nE < 0 || nC > (1 << 28) || nP > (1ll << 30)) { err = "bad problem size"; return BA_ERR_ARG; }
+  std::vector<int64_t> deg(nP, 0);
+  for (int64_t e = 0; e < nE; ++e) {
+    if (cam_idx[e] < 0 || cam_idx[e] >= nC || pt_idx[e] < 0 || pt_idx[e] >= nP) { err = "vertex index out of range"; return BA_ERR_ARG; }
+    deg[pt_idx[e]]++;
+  }
+  std::vector<int64_t> cuts(opt.world_size + 1);
+  partition_points(nP, deg.data(), opt.world_size, cuts.data());
+  g.pt_begin = cuts[opt.rank];
+  g.pt_end = cuts[opt.rank + 1];
+  g.nPl = (int)(g.pt_end - g.pt_begin);
+  // local edges grouped by point (counting sort), then camera-ascending inside a point
+  std::vector<int64_t> ptr(g.nPl + 1, 0);
+  for (int p = 0; p < g.nPl; ++p) ptr[p + 1] = ptr[p] + deg[g.pt_begin + p];
+  const int64_t nEl = ptr[g.nPl];
+  if (nEl > (1ll << 31) - 4 * TE) { err = "too many observations on one rank"; return BA_ERR_ARG; }
+  g.nEl = (int)nEl;
+  std::vector<int64_t> order(nEl), fill(ptr.begin(), ptr.end() - 1);
+  for (int64_t e = 0; e < nE; ++e) {
+    const int64_t p = pt_idx[e];
+    if (p >= g.pt_begin && p < g.pt_end) order[fill[p - g.pt_begin]++] = e;
+  }
+  for (int p = 0; p < g.nPl; ++p)
+    std::sort(order.begin() + ptr[p], order.begin() + ptr[p + 1], [&](int64_t a, int64_t b) {
+      return cam_idx[a] != cam_idx[b] ? cam_idx[a] < cam_idx[b] : a < b;
+    });
+  // tiles
+  g.tile.clear();
+  g.pt_slot.assign(g.nPl, 0);
+  int slab = 0;
+  int cur_pt0 = 0, cur_np = 0, cur_ne = 0;
+  auto close_tile = [&]() {
+    if (cur_np > 0) {
+      g.tile.push_back(make_int4(slab * TE, cur_ne, cur_pt0, cur_np));
+      slab += 1;
+    }
+    cur_np = 0; cur_ne = 0;
+  };
+  for (int p = 0; p < g.nPl; ++p) {
+    const int64_t dg = ptr[p + 1] - ptr[p];
+    if (dg > TE) {
+      close_tile();
+      g.pt_slot[p] = slab * TE;
+      g.tile.push_back(make_int4(slab * TE, (int)dg, p, 1));
+      slab += (int)((dg + TE - 1) / TE);
+      continue;
+    }
+    if (cur_np > 0 && (cur_ne + dg > TE || cur_np == TE)) close_tile();
+    if (cur_np == 0) cur_pt0 = p;
+    g.pt_slot[p] = slab * TE + cur_ne;
+    cur_np += 1;
+    cur_ne += (int)dg;
+  }
+  close_tile();
+  g.nT = (int)g.tile.size();
+  g.nSlabs = slab;
+  const size_t nSlots = (size_t)slab * TE;
+  g.e_cam.assign(nSlots, 0);
+  g.e_lp.assign(nSlots, 0);
+  g.edge_of_slot.assign(nSlots, -1);
+  g.slot_of_edge.assign(nE, -1);
+  for (int t = 0; t < g.nT; ++t) {
+    const int4 td = g.tile[t];
+    for (int lp = 0; lp < td.w; ++lp) {
+      const int p = td.z + lp;
+      const int s0 = g.pt_slot[p];
+      for (int64_t k = ptr[p]; k < ptr[p + 1]; ++k) {
+        const int slot = s0 + (int)(k - ptr[p]);
+        const int64_t e = order[k];
+        g.e_cam[slot] = cam_idx[e];
+        g.e_lp[slot] = (unsigned short)lp;
+        g.edge_of_slot[slot] = e;
+        g.slot_of_edge[e] = slot;
+      }
+    }
+  }
+  // camera-major view of the local edges (slot-ascending inside a camera)
+  std::vector<int> cptr(nC + 1, 0);
+  for (size_t s = 0; s < nSlots; ++s)
+    if (g.edge_of_slot[s] >= 0) cptr[g.e_cam[s] + 1]++;
+  for (int64_t c = 0; c < nC; ++c) cptr[c + 1] += cptr[c];
+  g.cm_pt.assign(nEl, 0);
+  g.cm_slot.assign(nEl, 0);
+  {
+    std::vector<int> cf(cptr.begin(), cptr.end() - 1);
+    for (int t = 0; t < g.nT; ++t) {
+      const int4 td = g.tile[t];
+      for (int i = 0; i < td.y; ++i) {
+        const int slot = td.x + i;
+        const int c = g.e_cam[slot];
+        const int k = cf[c]++;
+        g.cm_pt[k] = td.z + g.e_lp[slot];
+        g.cm_slot[k] = slot;
+      }
+    }
+  }
+  g.chunk.clear();
+  g.cam_chunk_ptr.assign(nC + 1, 0);
+  for (int64_t c = 0; c < nC; ++c) {
+    for (int b = cptr[c]; b < cptr[c + 1]; b += CM_CHUNK)
+      g.chunk.push_back(make_int4((int)c, b, std::min(b + CM_CHUNK, cptr[c + 1]), 0));
+    g.cam_chunk_ptr[c + 1] = (int)g.chunk.size();
+  }
+  g.nChunks = (int)g.chunk.size();
+  return BA_OK;
+}
+
+struct EventPair { cudaEvent_t a, b; };
+
+struct Impl {
+  ba_options opt{};
+  HostGraph g;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+  bool comm_ready = false;
+  bool timing = false;
+  ba_stats stats{};
+  bool linearized = false, have_step = false;
+  double region = 1e3;
+  virtual ~Impl() {}
+  int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  virtual int init(const void *obs) = 0;
+  virtual int set_params(const void *cam, const void *pt) = 0;
+  virtual int get_params(void *cam, void *pt) = 0;
+  virtual int set_information(const void *info) = 0;
+  virtual int linearize(double *cost) = 0;
+  virtual int process_diag(double region, int recover) = 0;
+  virtual int solve(const ba_pcg_options *o, int *iters, int *done) = 0;
+  virtual int step_norms(double *dx, double *x) = 0;
+  virtual int eval_trial(double *cost_new, double *model_sq) = 0;
+  virtual int accept_step() = 0;
+  virtual int reject_step() = 0;
+  virtual int backup_step() = 0;
+  virtual int grad_inf(double *g) = 0;
+  virtual int read(int which, void *out) = 0;
+  virtual int write_dx(const void *dx) = 0;
+  virtual int eval_edges(void *r, void *J) = 0;
+  virtual int schur_apply(const void *p, void *q) = 0;
+  virtual int get_stats(ba_stats *out) = 0;
+  virtual int reset_stats() = 0;
+  virtual int algorithmic_bytes(double *a, double *b) = 0;
+};
+
+template <typename T>
+struct ImplT : Impl {
+  Dev<T> d{};
+  void *arena = nullptr;
+  size_t arena_bytes = 0;
+  T *e_info_dev = nullptr, *cm_info_dev = nullptr;
+  T *pt_full = nullptr;  // [3 nP] gather buffer, world_size > 1 only
+  double *h_scal = nullptr;
+  PcgState *h_st = nullptr;
+  std::vector<EventPair> ev_pool;
+  size_t ev_used = 0;
+  std::vector<size_t> ev_schur, ev_lin, ev_pcg, ev_solve;
+  int pcg_chunk = 8;
+
+  ~ImplT() override {
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto &e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (arena) cudaFree(arena);
+    if (e_info_dev) cudaFree(e_info_dev);
+    if (cm_info_dev) cudaFree(cm_info_dev);
+    if (pt_full) cudaFree(pt_full);
+    if (h_scal) cudaFreeHost(h_scal);
+    if (h_st) cudaFreeHost(h_st);
+    if (comm_ready) ncclCommDestroy(comm);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // ---- timing helpers -------------------------------------------------------
+  size_t ev_begin() {
+    if (ev_used == ev_pool.size()) {
+      EventPair p;
+      cudaEventCreate(&p.a);
+      cudaEventCreate(&p.b);
+      ev_pool.push_back(p);
+    }
+    cudaEventRecord(ev_pool[ev_used].a, stream);
+    return ev_used++;
+  }
+  void ev_end(size_t i) { cudaEventRecord(ev_pool[i].b, stream); }
+  double ev_sum(std::vector<size_t> &v) {
+    double tot = 0;
+    for (size_t i : v) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev_pool[i].a, ev_pool[i].b);
+      tot += ms;
+    }
+    v.clear();
+    return tot;
+  }
+  void fold_events() {
+    cudaStreamSynchronize(stream);
+    stats.schur_apply_ms += ev_sum(ev_schur);
+    stats.linearize_ms += ev_sum(ev_lin);
+    stats.pcg_loop_ms += ev_sum(ev_pcg);
+    stats.solve_ms += ev_sum(ev_solve);
+    ev_used = 0;
+  }
+
+  // ---- collectives ----------------------------------------------------------
+  int allreduce_T(T *p, size_t n) {
+    if (opt.world_size == 1) return BA_OK;
+    if (!comm_ready) return fail(BA_ERR_STATE, "world_size > 1 but ba_comm_init was not called");
+    BA_NCCL(ncclAllReduce(p, p, n, NcclType<T>::v, ncclSum, comm, stream));
+    return BA_OK;
+  }
+  int allreduce_scal(int first, int n, ncclRedOp_t op) {
+    if (opt.world_size == 1) return BA_OK;
+    if (!comm_ready) return fail(BA_ERR_STATE, "world_size > 1 but ba_comm_init was not called");
+    BA_NCCL(ncclAllReduce(d.scal + first, d.scal + first, n, ncclDouble, op, comm, stream));
+    return BA_OK;
+  }
+  int fetch_scalars() {
+    BA_CUDA(cudaMemcpyAsync(h_scal, d.scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, stream));
+    BA_CUDA(cudaStreamSynchronize(stream));
+    return BA_OK;
+  }
+
+  // ---- set-up -----------------------------------------------------------------
+  int init(const void *obs_v) override {
+    const T *obs = (const T *)obs_v;
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const int K = opt.compute_kind == BA_IMPLICIT ? 24 : 27;
+    const size_t nSlots = (size_t)g.nSlabs * TE, nC = g.nC, nPl = g.nPl, nEl = g.nEl;
+    const size_t nPart = std::max<size_t>({(size_t)g.nT * 2, (size_t)AUX_GRID * 4, 64});
+    // arena carving
+    struct Item { void **ptr; size_t bytes; };
+    std::vector<Item> items;
+    int4 *tile, *chunk; int *e_cam, *pt_slot, *cam_chunk_ptr, *cm_pt; unsigned short *e_lp; T *e_obs, *cm_obs;
+    auto add = [&](auto **p, size_t count) { items.push_back({(void **)p, count * sizeof(**p)}); };
+    add(&tile, g.nT); add(&e_cam, nSlots); add(&e_lp, nSlots); add(&e_obs, 2 * nSlots); add(&pt_slot, nPl);
+    add(&chunk, g.nChunks); add(&cam_chunk_ptr, nC + 1); add(&cm_pt, nEl); add(&cm_obs, 2 * nEl);
+    add(&d.cam, 9 * nC); add(&d.pt, 3 * nPl);
+    add(&d.Hpp, 90 * nC);  // Hpp followed by gc
+    add(&d.Hll, 9 * nPl); add(&d.gl, 3 * nPl);
+    add(&d.WJ, (size_t)K * nSlots);
+    add(&d.cm_part, (size_t)g.nChunks * 54);
+    add(&d.HppD, 81 * nC); add(&d.HppInv, 81 * nC); add(&d.HllInv, 9 * nPl); add(&d.w, 3 * nPl);
+    add(&d.dxc, 9 * nC); add(&d.dxl, 3 * nPl); add(&d.dxc_bk, 9 * nC); add(&d.dxl_bk, 3 * nPl);
+    add(&d.sA, 18 * nC);  // sA followed by sB
+    add(&d.r, 9 * nC); add(&d.p, 9 * nC); add(&d.q, 9 * nC); add(&d.z, 9 * nC); add(&d.xbk, 9 * nC);
+    add(&d.st, 1); add(&d.scal, S_COUNT); add(&d.partials, nPart);
+    size_t total = 0;
+    for (auto &it : items) total += (it.bytes + 255) / 256 * 256 + 256;
+    BA_CUDA(cudaMalloc(&arena, total));
+    arena_bytes = total;
+    BA_CUDA(cudaMemsetAsync(arena, 0, total, stream));
+    size_t off = 0;
+    for (auto &it : items) {
+      *it.ptr = (char *)arena + off;
+      off += (it.bytes + 255) / 256 * 256 + 256;
+    }
+    d.gc = d.Hpp + 81 * nC;
+    d.sB = d.sA + 9 * nC;
+    d.nC = (int)nC; d.nPl = (int)nPl; d.nT = g.nT; d.nSlabs = g.nSlabs; d.nChunks = g.nChunks; d.nEl = g.nEl;
+    d.implicit = opt.compute_kind == BA_IMPLICIT;
+    d.tile = tile; d.e_cam = e_cam; d.e_lp = e_lp; d.e_obs = e_obs; d.e_info = nullptr; d.pt_slot = pt_slot;
+    d.chunk = chunk; d.cam_chunk_ptr = cam_chunk_ptr; d.cm_pt = cm_pt; d.cm_obs = cm_obs; d.cm_info = nullptr;
+    d.damp = 1. / region;
+    // upload the static graph
+    std::vector<T> h_obs(2 * nSlots, T(0)), h_cm_obs(2 * nEl);
+    for (size_t s = 0; s < nSlots; ++s) {
+      const int64_t e = g.edge_of_slot[s];
+      if (e >= 0) { h_obs[2 * s] = obs[2 * e]; h_obs[2 * s + 1] = obs[2 * e + 1]; }
+    }
+    for (size_t k = 0; k < nEl; ++k) {
+      const int64_t e = g.edge_of_slot[g.cm_slot[k]];
+      h_cm_obs[2 * k] = obs[2 * e];
+      h_cm_obs[2 * k + 1] = obs[2 * e + 1];
+    }
+    auto up = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+      return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream) : cudaSuccess;
+    };
+    BA_CUDA(up(tile, g.tile.data(), sizeof(int4) * g.nT));
+    BA_CUDA(up(e_cam, g.e_cam.data(), sizeof(int) * nSlots));
+    BA_CUDA(up(e_lp, g.e_lp.data(), sizeof(unsigned short) * nSlots));
+    BA_CUDA(up(e_obs, h_obs.data(), sizeof(T) * 2 * nSlots));
+    BA_CUDA(up(pt_slot, g.pt_slot.data(), sizeof(int) * nPl));
+    BA_CUDA(up(chunk, g.chunk.data(), sizeof(int4) * g.nChunks));
+    BA_CUDA(up(cam_chunk_ptr, g.cam_chunk_ptr.data(), sizeof(int) * (nC + 1)));
+    BA_CUDA(up(cm_pt, g.cm_pt.data(), sizeof(int) * nEl));
+    BA_CUDA(up(cm_obs, h_cm_obs.data(), sizeof(T) * 2 * nEl));
+    BA_CUDA(cudaHostAlloc(&h_scal, sizeof(double) * S_COUNT, cudaHostAllocDefault));
+    BA_CUDA(cudaHostAlloc(&h_st, sizeof(PcgState), cudaHostAllocDefault));
+    if (opt.world_size > 1) BA_CUDA(cudaMalloc(&pt_full, sizeof(T) * 3 * g.nP));
+    BA_CUDA(cudaStreamSynchronize(stream));
+    // free the big host staging vectors that are no longer needed
+    std::vector<int>().swap(g.e_cam);
+    std::vector<unsigned short>().swap(g.e_lp);
+    std::vector<int>().swap(g.cm_pt);
+    return BA_OK;
+  }
+
+  int set_params(const void *cam_v, const void *pt_v) override {
+    if (!cam_v || !pt_v) return fail(BA_ERR_ARG, "null parameter buffer");
+    BA_CUDA(cudaSetDevice(opt.device));
+    const T *cam = (const T *)cam_v, *pt = (const T *)pt_v;
+    BA_CUDA(cudaMemcpyAsync(d.cam, cam, sizeof(T) * 9 * g.nC, cudaMemcpyHostToDevice, stream));
+    if (g.nPl)
+      BA_CUDA(cudaMemcpyAsync(d.pt, pt + 3 * g.pt_begin, sizeof(T) * 3 * g.nPl, cudaMemcpyHostToDevice, stream));
+    // a new parameter vector is a new problem: deltaX starts at zero (allocateResourceCUDA memset,
+    // schur_LM_linear_system.cu:37)
+    BA_CUDA(cudaMemsetAsync(d.dxc, 0, sizeof(T) * 9 * g.nC, stream));
+    BA_CUDA(cudaMemsetAsync(d.dxc_bk, 0, sizeof(T) * 9 * g.nC, stream));
+    if (g.nPl) {
+      BA_CUDA(cudaMemsetAsync(d.dxl, 0, sizeof(T) * 3 * g.nPl, stream));
+      BA_CUDA(cudaMemsetAsync(d.dxl_bk, 0, sizeof(T) * 3 * g.nPl, stream));
+    }
+    BA_CUDA(cudaStreamSynchronize(stream));
+    linearized = false;
+    have_step = false;
+    return BA_OK;
+  }
+
+  int get_params(void *cam_v, void *pt_v) override {
+    if (!cam_v || !pt_v) return fail(BA_ERR_ARG, "null parameter buffer");
+    BA_CUDA(cudaSetDevice(opt.device));
+    T *cam = (T *)cam_v, *pt = (T *)pt_v;
+    BA_CUDA(cudaMemcpyAsync(cam, d.cam, sizeof(T) * 9 * g.nC, cudaMemcpyDeviceToHost, stream));
+    if (opt.world_size == 1) {
+      BA_CUDA(cudaMemcpyAsync(pt, d.pt, sizeof(T) * 3 * g.nP, cudaMemcpyDeviceToHost, stream));
+    } else {
+      // every rank owns a contiguous point range: zero-fill + allreduce(sum) = allgatherv
+      BA_CUDA(cudaMemsetAsync(pt_full, 0, sizeof(T) * 3 * g.nP, stream));
+      if (g.nPl)
+        BA_CUDA(cudaMemcpyAsync(pt_full + 3 * g.pt_begin, d.pt, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
+      BA_TRY(allreduce_T(pt_full, 3 * (size_t)g.nP));
+      BA_CUDA(cudaMemcpyAsync(pt, pt_full, sizeof(T) * 3 * g.nP, cudaMemcpyDeviceToHost, stream));
+    }
+    BA_CUDA(cudaStreamSynchronize(stream));
+    return BA_OK;
+  }
+
+  int set_information(const void *info_v) override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    if (!info_v) {
+      d.e_info = nullptr;
+      d.cm_info = nullptr;
+      linearized = false;
+      return BA_OK;
+    }
+    if (opt.compute_kind == BA_IMPLICIT)
+      return fail(BA_ERR_ARG, "information matrices are not supported in implicit mode "
+                              "(the reference's implicit build ignores them, build_implicit_linear_system.cu:272-274)");
+    const T *info = (const T *)info_v;
+    const size_t nSlots = (size_t)g.nSlabs * TE, nEl = g.nEl;
+    std::vector<T> h_e(4 * nSlots, T(0)), h_c(4 * nEl);
+    for (size_t s = 0; s < nSlots; ++s) {
+      const int64_t e = g.edge_of_slot[s];
+      if (e >= 0) for (int k = 0; k < 4; ++k) h_e[4 * s + k] = info[4 * e + k];
+    }
+    for (size_t k = 0; k < nEl; ++k) {
+      const int64_t e = g.edge_of_slot[g.cm_slot[k]];
+      for (int q = 0; q < 4; ++q) h_c[4 * k + q] = info[4 * e + q];
+    }
+    if (!e_info_dev) {
+      BA_CUDA(cudaMalloc(&e_info_dev, sizeof(T) * std::max<size_t>(4 * nSlots, 4)));
+      BA_CUDA(cudaMalloc(&cm_info_dev, sizeof(T) * std::max<size_t>(4 * nEl, 4)));
+    }
+    BA_CUDA(cudaMemcpyAsync(e_info_dev, h_e.data(), sizeof(T) * 4 * nSlots, cudaMemcpyHostToDevice, stream));
+    BA_CUDA(cudaMemcpyAsync(cm_info_dev, h_c.data(), sizeof(T) * 4 * nEl, cudaMemcpyHostToDevice, stream));
+    BA_CUDA(cudaStreamSynchronize(stream));
+    d.e_info = e_info_dev;
+    d.cm_info = cm_info_dev;
+    linearized = false;
+    return BA_OK;
+  }
+
+  // ---- HP1 --------------------------------------------------------------------
+  int linearize(double *cost) override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    size_t ev = 0;
+    if (timing) ev = ev_begin();
+    BA_CUDA(launch_linearize<T>(d, stream));
+    stats.launches += launches_of_linearize();
+    stats.linearize_calls += 1;
+    BA_TRY(allreduce_T(d.Hpp, 90 * (size_t)g.nC));
+    BA_TRY(allreduce_scal(S_COST, 1, ncclSum));
+    if (timing) { ev_end(ev); ev_lin.push_back(ev); }
+    BA_TRY(fetch_scalars());
+    if (cost) *cost = h_scal[S_COST];
+    linearized = true;
+    return BA_OK;
+  }
+
+  int process_diag(double region_, int /*recover*/) override {
+    if (!(region_ > 0)) return fail(BA_ERR_ARG, "region must be positive");
+    region = region_;
+    d.damp = 1. / region_;
+    return BA_OK;
+  }
+
+  // ---- HP2 --------------------------------------------------------------------
+  int schur_edge(int mode, const T *xin, T *sout, int check_active, bool timed) {
+    size_t ev = 0;
+    if (timing && timed) ev = ev_begin();
+    BA_CUDA(launch_schur_edge<T>(d, mode, xin, sout, check_active, stream));
+    if (timing && timed) { ev_end(ev); ev_schur.push_back(ev); }
+    stats.launches += d.nT > 0 ? 1 : 0;
+    if (timed) stats.schur_apply_calls += 1;
+    return BA_OK;
+  }
+
+  int solve(const ba_pcg_options *o, int *iters, int *done) override {
+    if (!o) return fail(BA_ERR_ARG, "null pcg options");
+    if (!linearized) return fail(BA_ERR_STATE, "ba_solve before ba_linearize");
+    BA_CUDA(cudaSetDevice(opt.device));
+    size_t ev_s = 0, ev_p = 0;
+    if (timing) ev_s = ev_begin();
+    BA_CUDA(cudaMemsetAsync(d.sA, 0, sizeof(T) * 18 * g.nC, stream));
+    BA_CUDA(launch_prep<T>(d, stream));
+    stats.launches += launches_of_prep();
+    BA_TRY(schur_edge(SM_MAKEV, nullptr, d.sA, 0, false));  // sA = Hpl w
+    BA_TRY(schur_edge(SM_FULL, d.dxc, d.sB, 0, true));      // sB = Hpl Hll^-1 Hlp x0
+    BA_TRY(allreduce_T(d.sA, 18 * (size_t)g.nC));
+    BA_CUDA(launch_pcg_init<T>(d, o->max_iter, o->tol, o->refuse_ratio, stream));
+    stats.launches += 1;
+    if (timing) ev_p = ev_begin();
+    int launched = 0, n_seen = 0;
+    while (launched < o->max_iter) {
+      const int n = std::min(pcg_chunk, o->max_iter - launched);
+      const size_t ev_mark = ev_schur.size();
+      for (int i = 0; i < n; ++i) {
+        BA_TRY(schur_edge(SM_FULL, d.p, d.sB, 1, true));
+        BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
+        BA_CUDA(launch_pcg_step<T>(d, stream));
+        stats.launches += 1;
+      }
+      launched += n;
+      BA_CUDA(cudaMemcpyAsync(h_st, d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+      BA_CUDA(cudaStreamSynchronize(stream));
+      // edge launches issued after the loop ended returned immediately: keep only the
+      // event pairs of iterations that really ran
+      if (timing) ev_schur.resize(ev_mark + (size_t)(h_st->n - n_seen));
+      n_seen = h_st->n;
+      if (!h_st->active) break;
+    }
+    if (o->max_iter <= 0) {
+      BA_CUDA(cudaMemcpyAsync(h_st, d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+      BA_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); }
+    // inactive edge launches return immediately; only executed iterations are counted
+    stats.schur_apply_calls -= (launched - h_st->n);
+    BA_TRY(schur_edge(SM_BACKSUB, d.dxc, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
+    if (timing) { ev_end(ev_s); ev_solve.push_back(ev_s); }
+    stats.pcg_iters += h_st->n;
+    if (iters) *iters = h_st->n;
+    if (done) *done = h_st->done;
+    have_step = true;
+    return BA_OK;
+  }
+
+  int step_norms(double *dxn, double *xn) override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_CUDA(launch_norms<T>(d, stream));
+    stats.launches += 2;
+    BA_TRY(allreduce_scal(S_DX2_PT, 2, ncclSum));
+    BA_TRY(fetch_scalars());
+    if (dxn) *dxn = std::sqrt(h_scal[S_DX2_PT] + h_scal[S_DX2_CAM]);
+    if (xn) *xn = std::sqrt(h_scal[S_X2_PT] + h_scal[S_X2_CAM]);
+    return BA_OK;
+  }
+
+  int eval_trial(double *cost_new, double *model_sq) override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_CUDA(launch_trial<T>(d, stream));
+    stats.launches += 2;
+    BA_TRY(allreduce_scal(S_TRIAL_COST, 2, ncclSum));
+    BA_TRY(fetch_scalars());
+    if (cost_new) *cost_new = h_scal[S_TRIAL_COST];
+    if (model_sq) *model_sq = h_scal[S_MODEL_SQ];
+    return BA_OK;
+  }
+
+  int accept_step() override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_CUDA(launch_apply_step<T>(d, stream));
+    stats.launches += 1;
+    linearized = false;
+    return BA_OK;
+  }
+
+  int reject_step() override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_CUDA(cudaMemcpyAsync(d.dxc, d.dxc_bk, sizeof(T) * 9 * g.nC, cudaMemcpyDeviceToDevice, stream));
+    if (g.nPl) BA_CUDA(cudaMemcpyAsync(d.dxl, d.dxl_bk, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
+    return BA_OK;
+  }
+
+  int backup_step() override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_CUDA(cudaMemcpyAsync(d.dxc_bk, d.dxc, sizeof(T) * 9 * g.nC, cudaMemcpyDeviceToDevice, stream));
+    if (g.nPl) BA_CUDA(cudaMemcpyAsync(d.dxl_bk, d.dxl, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
+    return BA_OK;
+  }
+
+  int grad_inf(double *gi) override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_CUDA(launch_ginf<T>(d, stream));
+    stats.launches += 2;
+    BA_TRY(allreduce_scal(S_GINF, 1, ncclMax));
+    BA_TRY(fetch_scalars());
+    if (gi) *gi = h_scal[S_GINF];
+    return BA_OK;
+  }
+
+  // ---- inspection -------------------------------------------------------------
+  int read(int which, void *out_v) override {
+    if (!out_v) return fail(BA_ERR_ARG, "null output buffer");
+    BA_CUDA(cudaSetDevice(opt.device));
+    T *out = (T *)out_v;
+    const size_t nC = g.nC, nP = g.nP, nPl = g.nPl, pb = g.pt_begin;
+    switch (which) {
+      case BA_BUF_HPP:
+        BA_CUDA(cudaMemcpyAsync(out, d.Hpp, sizeof(T) * 81 * nC, cudaMemcpyDeviceToHost, stream));
+        break;
+      case BA_BUF_HLL:
+        memset(out, 0, sizeof(T) * 9 * nP);
+        if (nPl) BA_CUDA(cudaMemcpyAsync(out + 9 * pb, d.Hll, sizeof(T) * 9 * nPl, cudaMemcpyDeviceToHost, stream));
+        break;
+      case BA_BUF_G:
+        memset(out, 0, sizeof(T) * (9 * nC + 3 * nP));
+        BA_CUDA(cudaMemcpyAsync(out, d.gc, sizeof(T) * 9 * nC, cudaMemcpyDeviceToHost, stream));
+        if (nPl) BA_CUDA(cudaMemcpyAsync(out + 9 * nC + 3 * pb, d.gl, sizeof(T) * 3 * nPl, cudaMemcpyDeviceToHost, stream));
+        break;
+      case BA_BUF_DX:
+        memset(out, 0, sizeof(T) * (9 * nC + 3 * nP));
+        BA_CUDA(cudaMemcpyAsync(out, d.dxc, sizeof(T) * 9 * nC, cudaMemcpyDeviceToHost, stream));
+        if (nPl) BA_CUDA(cudaMemcpyAsync(out + 9 * nC + 3 * pb, d.dxl, sizeof(T) * 3 * nPl, cudaMemcpyDeviceToHost, stream));
+        break;
+      case BA_BUF_W:
+      case BA_BUF_J: {
+        const int K = d.implicit ? 24 : 27;
+        if ((which == BA_BUF_W) == (bool)d.implicit)
+          return fail(BA_ERR_STATE, "BA_BUF_W exists in explicit mode, BA_BUF_J in implicit mode");
+        const size_t nSlots = (size_t)g.nSlabs * TE;
+        std::vector<T> h((size_t)K * nSlots);
+        if (nSlots) BA_CUDA(cudaMemcpyAsync(h.data(), d.WJ, sizeof(T) * K * nSlots, cudaMemcpyDeviceToHost, stream));
+        BA_CUDA(cudaStreamSynchronize(stream));
+        for (int64_t e = 0; e < g.nE; ++e) {
+          const int slot = g.slot_of_edge[e];
+          for (int k = 0; k < K; ++k)
+            out[(size_t)K * e + k] = slot < 0 ? T(0) : h[(size_t)(slot / TE) * K * TE + (size_t)k * TE + slot % TE];
+        }
+        break;
+      }
+      default:
+        return fail(BA_ERR_ARG, "unknown buffer id %d", which);
+    }
+    BA_CUDA(cudaStreamSynchronize(stream));
+    return BA_OK;
+  }
+
+  int write_dx(const void *dx_v) override {
+    if (!dx_v) return fail(BA_ERR_ARG, "null dx");
+    BA_CUDA(cudaSetDevice(opt.device));
+    const T *dx = (const T *)dx_v;
+    BA_CUDA(cudaMemcpyAsync(d.dxc, dx, sizeof(T) * 9 * g.nC, cudaMemcpyHostToDevice, stream));
+    if (g.nPl)
+      BA_CUDA(cudaMemcpyAsync(d.dxl, dx + 9 * g.nC + 3 * g.pt_begin, sizeof(T) * 3 * g.nPl, cudaMemcpyHostToDevice, stream));
+    BA_CUDA(cudaStreamSynchronize(stream));
+    return BA_OK;
+  }
+
+  int eval_edges(void *r_v, void *J_v) override {
+    if (!r_v) return fail(BA_ERR_ARG, "null residual buffer");
+    BA_CUDA(cudaSetDevice(opt.device));
+    const size_t nSlots = (size_t)g.nSlabs * TE;
+    T *dr = nullptr, *dJ = nullptr;
+    BA_CUDA(cudaMalloc(&dr, sizeof(T) * std::max<size_t>(2 * nSlots, 2)));
+    if (J_v) BA_CUDA(cudaMalloc(&dJ, sizeof(T) * std::max<size_t>(24 * nSlots, 24)));
+    cudaError_t e = launch_eval_edges<T>(d, dr, dJ, stream);
+    stats.launches += 1;
+    std::vector<T> hr(2 * nSlots), hJ(J_v ? 24 * nSlots : 0);
+    if (e == cudaSuccess && nSlots) e = cudaMemcpyAsync(hr.data(), dr, sizeof(T) * 2 * nSlots, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && J_v && nSlots) e = cudaMemcpyAsync(hJ.data(), dJ, sizeof(T) * 24 * nSlots, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(dr);
+    if (dJ) cudaFree(dJ);
+    BA_CUDA(e);
+    T *r = (T *)r_v, *J = (T *)J_v;
+    for (int64_t ed = 0; ed < g.nE; ++ed) {
+      const int slot = g.slot_of_edge[ed];
+      for (int k = 0; k < 2; ++k) r[2 * ed + k] = slot < 0 ? T(0) : hr[2 * (size_t)slot + k];
+      if (J) for (int k = 0; k < 24; ++k) J[24 * ed + k] = slot < 0 ? T(0) : hJ[24 * (size_t)slot + k];
+    }
+    return BA_OK;
+  }
+
+  int schur_apply(const void *p_v, void *q_v) override {
+    if (!p_v || !q_v) return fail(BA_ERR_ARG, "null vector");
+    if (!linearized) return fail(BA_ERR_STATE, "ba_schur_apply before ba_linearize");
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_CUDA(launch_prep<T>(d, stream));
+    stats.launches += launches_of_prep();
+    BA_CUDA(cudaMemsetAsync(d.sB, 0, sizeof(T) * 9 * g.nC, stream));
+    BA_CUDA(cudaMemcpyAsync(d.z, p_v, sizeof(T) * 9 * g.nC, cudaMemcpyHostToDevice, stream));
+    BA_TRY(schur_edge(SM_FULL, d.z, d.sB, 0, true));
+    BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
+    BA_CUDA(launch_cam_matvec_sub<T>(d, d.z, d.sB, d.q, stream));
+    stats.launches += 1;
+    BA_CUDA(cudaMemcpyAsync(q_v, d.q, sizeof(T) * 9 * g.nC, cudaMemcpyDeviceToHost, stream));
+    BA_CUDA(cudaMemsetAsync(d.sB, 0, sizeof(T) * 9 * g.nC, stream));
+    BA_CUDA(cudaStreamSynchronize(stream));
+    return BA_OK;
+  }
+
+  int get_stats(ba_stats *out) override {
+    if (!out) return fail(BA_ERR_ARG, "null stats");
+    BA_CUDA(cudaSetDevice(opt.device));
+    fold_events();
+    *out = stats;
+    return BA_OK;
+  }
+  int reset_stats() override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    fold_events();
+    stats = ba_stats{};
+    return BA_OK;
+  }
+
+  // A_pcg = nE(27s+4) + nP(9s+4) + nC 216 s  (24s for implicit);
+  // A_lin = nE(8+29s) + nP 15 s + nC 99 s  (26s implicit).  Per rank: local nE, nP.
+  int algorithmic_bytes(double *a, double *b) override {
+    const double s = sizeof(T), nE = g.nEl, nP = g.nPl, nC = g.nC;
+    const double kw = d.implicit ? 24. : 27.;
+    if (a) *a = nE * (kw * s + 4.) + nP * (9. * s + 4.) + nC * 216. * s;
+    if (b) *b = nE * (8. + (kw + 2.) * s) + nP * 15. * s + nC * 99. * s;
+    return BA_OK;
+  }
+};
+
+}  // namespace ba
+
+// ==================================================================================
+// C-ABI
+struct ba_solver {
+  std::unique_ptr<ba::Impl> impl;
+};
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+int ba_abi_version(void) { return MEGBA_B200_ABI_VERSION; }
+
+int ba_partition_points(int64_t nP, const int64_t *pt_degree, int32_t world_size, int64_t *pt_begin) {
+  return ba::partition_points(nP, pt_degree, world_size, pt_begin);
+}
+
+int ba_create(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx,
+              const int32_t *pt_idx, const void *obs, ba_solver **out) {
+  if (!opt || !out || (nE > 0 && (!cam_idx || !pt_idx || !obs))) return BA_ERR_ARG;
+  *out = nullptr;
+  if (opt->world_size < 1 || opt->rank < 0 || opt->rank >= opt->world_size) return BA_ERR_ARG;
+  if (opt->dtype != BA_F64 && opt->dtype != BA_F32) return BA_ERR_ARG;
+  if (opt->compute_kind != BA_EXPLICIT && opt->compute_kind != BA_IMPLICIT) return BA_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device: megba_b200 has no CPU fallback";
+    return BA_ERR_NO_DEVICE;
+  }
+  if (opt->device < 0 || opt->device >= ndev) return BA_ERR_ARG;
+  std::unique_ptr<ba::Impl> impl;
+  if (opt->dtype == BA_F64) impl.reset(new ba::ImplT<double>());
+  else impl.reset(new ba::ImplT<float>());
+  impl->opt = *opt;
+  int rc = ba::build_host_graph(*opt, nC, nP, nE, cam_idx, pt_idx, impl->g, impl->err);
+  if (rc != BA_OK) { g_create_error = impl->err; return rc; }
+  rc = impl->init(obs);
+  if (rc != BA_OK) { g_create_error = impl->err; return rc; }
+  *out = new ba_solver{std::move(impl)};
+  return BA_OK;
+}
+
+void ba_destroy(ba_solver *s) {
+  if (!s) return;
+  if (s->impl) cudaSetDevice(s->impl->opt.device);
+  delete s;
+}
+
+const char *ba_last_error(const ba_solver *s) { return s ? s->impl->err.c_str() : g_create_error.c_str(); }
+
+int ba_comm_unique_id(void *id128) {
+  if (!id128) return BA_ERR_ARG;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return BA_ERR_NCCL;
+  memcpy(id128, &id, sizeof id);
+  return BA_OK;
+}
+
+int ba_comm_init(ba_solver *s, const void *id128) {
+  if (!s || !id128) return BA_ERR_ARG;
+  ba::Impl *m = s->impl.get();
+  if (m->opt.world_size == 1) return BA_OK;
+  if (cudaSetDevice(m->opt.device) != cudaSuccess) return m->fail(BA_ERR_CUDA, "cudaSetDevice");
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclResult_t r = ncclCommInitRank(&m->comm, m->opt.world_size, id, m->opt.rank);
+  if (r != ncclSuccess) return m->fail(BA_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
+  m->comm_ready = true;
+  return BA_OK;
+}
+
+#define BA_FWD(call) \
+  if (!s) return BA_ERR_ARG; \
+  return s->impl->call
+
+int ba_set_params(ba_solver *s, const void *cam, const void *pt) { BA_FWD(set_params(cam, pt)); }
+int ba_get_params(ba_solver *s, void *cam, void *pt) { BA_FWD(get_params(cam, pt)); }
+int ba_set_information(ba_solver *s, const void *info) { BA_FWD(set_information(info)); }
+int ba_linearize(ba_solver *s, double *cost) { BA_FWD(linearize(cost)); }
+int ba_process_diag(ba_solver *s, double region, int recover) { BA_FWD(process_diag(region, recover)); }
+int ba_solve(ba_solver *s, const ba_pcg_options *o, int32_t *iters, int32_t *done) { BA_FWD(solve(o, iters, done)); }
+int ba_step_norms(ba_solver *s, double *a, double *b) { BA_FWD(step_norms(a, b)); }
+int ba_eval_trial(ba_solver *s, double *a, double *b) { BA_FWD(eval_trial(a, b)); }
+int ba_accept_step(ba_solver *s) { BA_FWD(accept_step()); }
+int ba_reject_step(ba_solver *s) { BA_FWD(reject_step()); }
+int ba_grad_inf_norm(ba_solver *s, double *g) { BA_FWD(grad_inf(g)); }
+int ba_read(ba_solver *s, int32_t which, void *out) { BA_FWD(read(which, out)); }
+int ba_write_dx(ba_solver *s, const void *dx) { BA_FWD(write_dx(dx)); }
+int ba_eval_edges(ba_solver *s, void *r, void *J) { BA_FWD(eval_edges(r, J)); }
+int ba_schur_apply(ba_solver *s, const void *p, void *q) { BA_FWD(schur_apply(p, q)); }
+int ba_get_stats(ba_solver *s, ba_stats *out) { BA_FWD(get_stats(out)); }
+int ba_reset_stats(ba_solver *s) { BA_FWD(reset_stats()); }
+int ba_algorithmic_bytes(ba_solver *s, double *a, double *b) { BA_FWD(algorithmic_bytes(a, b)); }
+
+int ba_set_timing(ba_solver *s, int32_t on) {
+  if (!s) return BA_ERR_ARG;
+  s->impl->timing = on != 0;
+  return BA_OK;
+}
+
+void *ba_stream(ba_solver *s) { return s ? (void *)s->impl->stream : nullptr; }
+
+// LMAlgo::solveCUDA, src/algo/lm_algo.cu:139-223 (line numbers in comments below)
+int ba_lm_solve(ba_solver *s, const ba_lm_options *lm, const ba_pcg_options *pcg, ba_lm_trace *trace,
+                int32_t trace_cap, int32_t *n_trace, int32_t verbose) {
+  if (!s || !lm || !pcg) return BA_ERR_ARG;
+  ba::Impl *m = s->impl.get();
+  const auto t0 = std::chrono::steady_clock::now();
+  auto elapsed = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  int nt = 0;
+  auto push = [&](double cost, int acc, int it, double region, double dxn, double rho) {
+    if (trace && nt < trace_cap) trace[nt] = ba_lm_trace{cost, acc, it, region, dxn, rho, elapsed()};
+    ++nt;
+  };
+  const bool talk = verbose && m->opt.rank == 0;
+  double F_new = 0., F = 0.;
+  BA_TRY(m->linearize(&F_new));                                               // :145-148
+  double region = lm->initial_region;                                         // lm_algo.cpp:15
+  if (talk) printf("Start with error: %g, log error: %g, elapsed %lld ms\n", F_new / 2, std::log10(F_new / 2), (long long)elapsed());
+  push(F_new, 1, 0, region, 0., 0.);
+  bool stop = false, recover = false;
+  int k = 0;
+  double v = 2.;
+  BA_TRY(m->backup_step());                                                  // :155
+  while (!stop && k < lm->max_iter) {                                         // :163
+    ++k;
+    m->stats.lm_iters += 1;
+    BA_TRY(m->process_diag(region, recover));                                 // :165
+    int it = 0, done = 0;
+    BA_TRY(m->solve(pcg, &it, &done));                                        // :166-169
+    double dxn = 0., xn = 0.;
+    BA_TRY(m->step_norms(&dxn, &xn));                                         // :172-175
+    if (dxn <= lm->epsilon2 * (xn + lm->epsilon1)) {                          // :176-179
+      push(F_new, -1, it, region, dxn, 0.);
+      break;
+    }
+    double F_trial = 0., model_sq = 0.;
+    BA_TRY(m->eval_trial(&F_trial, &model_sq));                               // :180-185
+    const double rho_den = model_sq - F_new;                                  // :181-182
+    F = F_new;
+    F_new = F_trial;
+    const double rho = -(F - F_new) / rho_den;                                // :186
+    if (F > F_new) {                                                          // :187
+      BA_TRY(m->accept_step());                                               // :192-194 (x += dx, backup)
+      double F_chk = 0.;
+      BA_TRY(m->linearize(&F_chk));                                           // :189
+      if (talk) printf("Iter %d error: %g, log error: %g", k, F_new / 2, std::log10(F_new / 2));
+      region /= std::max(1. / 3., 1. - std::pow(2. * rho - 1., 3));           // :197-198
+      v = 2.;
+      recover = false;
+      double ginf = 0.;
+      BA_TRY(m->grad_inf(&ginf));                                             // :203-204
+      stop = ginf <= lm->epsilon1;                                            // :205
+      push(F_new, 1, it, region, dxn, rho);
+    } else {
+      if (talk) printf("Iter %d failed", k);                                  // :207
+      BA_TRY(m->reject_step());                                               // :208-209
+      F_new = F;                                                              // :210
+      region /= v;                                                            // :211
+      v *= 2.;
+      recover = true;
+      // H and g are untouched by our solve, so nothing else needs restoring
+      m->linearized = true;
+      push(F_new, 0, it, region, dxn, rho);
+    }
+    if (talk) printf(", elapsed %lld ms\n", (long long)elapsed());
+  }
+  if (talk) printf("Finished\n");
+  if (n_trace) *n_trace = nt;
+  return BA_OK;
+}
+
+}  // extern "C"

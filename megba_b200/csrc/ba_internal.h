@@ -1,0 +1,92 @@
+// ba_internal.h -- device-side data model shared by ba_kernels.cu and ba_api.cu.
+//
+// HBM layout (one rank).  Observations ("edges") owned by this rank are sorted
+// point-major and packed into TILES: a tile is a run of whole points whose edges fit
+// one slab of TE slots; a point with more than TE edges gets a run of slabs of its
+// own.  Slot s of slab b is edge-array index b*TE + i.  Per-slot arrays:
+//   e_cam[slot] int32, e_lp[slot] uint16 (point index inside the tile),
+//   e_obs[slot][2], W/J blocked SoA: value k of slot (b,i) at  b*K*TE + k*TE + i
+//   (K = 27 for the explicit Hpl block, 24 for the implicit Jacobian), so a warp reads
+//   32 consecutive scalars per k and a whole slab is one contiguous K*TE*sizeof(T) run.
+// Points of this rank are numbered locally 0..nPl-1 (global id - pt_begin).
+// A second, camera-major view of the same edges (cm_*) feeds the atomic-free
+// accumulation of Hpp / g_c.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ba {
+
+constexpr int TE = 256;       // slots per slab == threads of the edge kernels
+constexpr int CM_CHUNK = 1024;  // edges per camera-major work item
+constexpr int CM_THREADS = 128;
+constexpr int NTRI = 45;       // upper triangle of a 9x9 block
+constexpr int AUX_GRID = 296;   // 2 CTAs per SM for the small grid-stride kernels
+
+struct PcgState {
+  double rho, rho_prev, rho_min, alpha, pq;
+  double tol, refuse;
+  int n, max_iter, active, done, refused, pad;
+};
+
+// device scalar slots (double) read back by the host
+enum Scal { S_COST = 0, S_TRIAL_COST = 1, S_MODEL_SQ = 2, S_DX2_PT = 3, S_X2_PT = 4, S_DX2_CAM = 5,
+            S_X2_CAM = 6, S_GINF = 7, S_COUNT = 16 };
+
+template <typename T>
+struct Dev {
+  // sizes
+  int nC, nPl, nT, nSlabs, nChunks, nEl;
+  int implicit;
+  // point-major static graph
+  const int4 *tile;             // {slot0, ne, pt0, np}
+  const int *e_cam;
+  const unsigned short *e_lp;
+  const T *e_obs;               // [slot][2]
+  const T *e_info;              // [slot][4] or nullptr
+  const int *pt_slot;           // [nPl] first slot of the point
+  // camera-major static graph
+  const int4 *chunk;            // {cam, beg, end, 0}
+  const int *cam_chunk_ptr;     // [nC+1]
+  const int *cm_pt;             // [nEl] local point index
+  const T *cm_obs;              // [nEl][2]
+  const T *cm_info;             // [nEl][4] or nullptr
+  // parameters
+  T *cam;                       // [nC][9]
+  T *pt;                        // [nPl][3]
+  // linear system (undamped)
+  T *Hpp, *gc;                  // [nC][81], [nC][9]   (contiguous: Hpp then gc)
+  T *Hll, *gl;                  // [nPl][9], [nPl][3]
+  T *WJ;                        // blocked SoA, K = 27 or 24
+  T *cm_part;                   // [nChunks][54]
+  // solve
+  T *HppD, *HppInv;             // [nC][81] damped block and its inverse
+  T *HllInv, *w;                // [nPl][9], [nPl][3]
+  T *dxc, *dxl;                 // step: [9nC], [3nPl]
+  T *dxc_bk, *dxl_bk;           // LM backup of the step (warm start after a reject)
+  T *sA, *sB;                   // [9nC] each, contiguous: edge-kernel scatter targets
+  T *r, *p, *q, *z, *xbk;       // PCG vectors [9nC]
+  PcgState *st;
+  double *scal;                 // [S_COUNT]
+  double *partials;             // per-CTA partial sums
+  double damp;                  // 1/region
+};
+
+// ---- launchers (ba_kernels.cu); all enqueue on `st` and return cudaGetLastError ----
+template <typename T> cudaError_t launch_linearize(const Dev<T> &d, cudaStream_t st);
+enum SchurMode { SM_FULL = 0, SM_MAKEV = 1, SM_BACKSUB = 2 };
+template <typename T> cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, int check_active,
+                                                    cudaStream_t st);
+template <typename T> cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_pcg_init(const Dev<T> &d, int max_iter, double tol, double refuse, cudaStream_t st);
+template <typename T> cudaError_t launch_pcg_step(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_trial(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_norms(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_apply_step(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_ginf(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_eval_edges(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st);
+template <typename T> cudaError_t launch_cam_matvec_sub(const Dev<T> &d, const T *p, const T *s, T *q, cudaStream_t st);
+int launches_of_linearize();
+int launches_of_prep();
+
+}  // namespace ba

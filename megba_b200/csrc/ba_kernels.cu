@@ -1,0 +1,863 @@
+// ba_kernels.cu -- sm_100a kernels of the LM / Schur-PCG hot path (fp64 and fp32).
+//
+// Reference functions replaced (see DESIGN.md for the full map):
+//   k_lin_pm / k_lin_cm / k_lin_cam_reduce   <- AnalyticalDerivativesKernelGradKernel
+//       (src/geo/analytical_derivatives.cu:162-285) fused with makeHSchur /
+//       makeHSchurWithInfo / makeHppHllSchur (src/edge/build_linear_system.cu:88-239,
+//       src/edge/build_implicit_linear_system.cu:65-111) and computeResidualNorm
+//       (src/algo/lm_algo.cu:26-51).  No global atomics: the point side is reduced
+//       inside a tile, the camera side by a second, camera-major pass.
+//   k_prep_points / k_prep_cams   <- processDiag kernels
+//       (src/linear_system/schur_LM_linear_system.cu:114-185) + cublasXmatinvBatched
+//       (src/solver/schur_pcg_solver.cu:61-97) + w = Hll^-1 g_l (:467-476).
+//   k_schur_edge   <- the two cusparseSpMV calls + oursGgemvBatched(Hll^-1) of one
+//       operator application (schur_pcg_solver.cu:315-357), MakeV (:430-510) and
+//       SolveW (:513-596); implicit operators implicitETMulx / implicitEMulx
+//       (src/solver/implicit_schur_pcg_solver.cu:21-90).  W (or J) is read ONCE.
+//   k_pcg_cam   <- all camera-space vector work of a PCG iteration
+//       (schur_pcg_solver.cu:265-313,359-406): one 8-CTA cluster, DSMEM reductions,
+//       scalars stay on the device (the reference syncs the host twice per iteration).
+//   k_trial   <- updateDeltaXTwoVertices + forward + JdxpF + reductions
+//       (src/edge/update.cu:14-41, src/algo/lm_algo.cu:61-126).
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "ba_geometry.cuh"
+#include "ba_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace ba {
+
+// --------------------------------------------------------------------------------
+// small helpers
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block; result valid in every thread.  sm: >= 32 entries.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *sm) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect sm from a previous use
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  T x = lane < nw ? sm[lane] : T(0);
+  x = warp_sum(x);
+  return x;
+}
+
+template <typename T>
+__device__ __forceinline__ size_t wj_base(int slot, int K) {
+  return (size_t)(slot / TE) * (size_t)(K * TE) + (size_t)(slot % TE);
+}
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+// per-edge evaluation shared by the linearisation kernels
+template <typename T>
+__device__ __forceinline__ void load_cam(const T *__restrict__ cam, int c, T *out) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[i] = __ldg(cam + 9 * (size_t)c + i);
+}
+
+// L = Omega * J rows (JMulInfo, build_linear_system.cu:149-176); identity when info == nullptr
+template <typename T>
+__device__ __forceinline__ void left_factor(const T *J, const T *info4, T *L) {
+#pragma unroll
+  for (int y = 0; y < 12; ++y) {
+    L[y] = J[y] * info4[0] + J[12 + y] * info4[2];
+    L[12 + y] = J[y] * info4[1] + J[12 + y] * info4[3];
+  }
+}
+
+// --------------------------------------------------------------------------------
+// HP1-A: point-major linearisation.  One CTA per tile, one thread per slot.
+template <typename T, bool IMPLICIT>
+__global__ void __launch_bounds__(TE) k_lin_pm(Dev<T> d) {
+  constexpr int K = IMPLICIT ? 24 : 27;
+  __shared__ T sh[12][TE];
+  __shared__ double red[32];
+  const int4 td = d.tile[blockIdx.x];
+  const int slot0 = td.x, ne = td.y, pt0 = td.z, np = td.w;
+  const int tid = threadIdx.x;
+  double cost = 0.;
+  T acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = T(0);
+  const bool big = ne > TE;
+  for (int base = 0; base < ne; base += TE) {
+    const int i = base + tid;
+    T hl[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) hl[k] = T(0);
+    if (i < ne) {
+      const int slot = slot0 + i;
+      const int c = d.e_cam[slot];
+      const int p = pt0 + (int)d.e_lp[slot];
+      T cm[9];
+      load_cam(d.cam, c, cm);
+      const T X0 = d.pt[3 * (size_t)p], X1 = d.pt[3 * (size_t)p + 1], X2 = d.pt[3 * (size_t)p + 2];
+      const typename Vec2<T>::type ob = reinterpret_cast<const typename Vec2<T>::type *>(d.e_obs)[slot];
+      T J[24], r0, r1;
+      const RotConst<T> rc = rot_const<T>(cm[0], cm[1], cm[2]);
+      edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+      cost += (double)(r0 * r0) + (double)(r1 * r1);
+      T Lb[24];
+      const T *L = J;
+      if (d.e_info) {
+        T om[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) om[k] = d.e_info[4 * (size_t)slot + k];
+        left_factor<T>(J, om, Lb);
+        L = Lb;
+      }
+      T *wj = d.WJ + wj_base<T>(slot, K);
+      if (IMPLICIT) {
+#pragma unroll
+        for (int k = 0; k < 24; ++k) wj[(size_t)k * TE] = J[k];
+      } else {
+#pragma unroll
+        for (int y = 0; y < 9; ++y)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) wj[(size_t)(3 * y + q) * TE] = L[y] * J[9 + q] + L[12 + y] * J[21 + q];
+      }
+#pragma unroll
+      for (int y = 0; y < 3; ++y) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) hl[3 * y + q] = L[9 + y] * J[9 + q] + L[21 + y] * J[21 + q];
+        hl[9 + y] = -(L[9 + y] * r0 + L[21 + y] * r1);
+      }
+    }
+    if (big) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc[k] += hl[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) sh[k][tid] = hl[k];
+    }
+  }
+  if (!big) {
+    __syncthreads();
+    if (tid < np) {
+      const int p = pt0 + tid;
+      const int s0 = d.pt_slot[p] - slot0;
+      const int s1 = (tid + 1 < np) ? d.pt_slot[p + 1] - slot0 : ne;
+      T sum[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) sum[k] = T(0);
+      for (int s = s0; s < s1; ++s) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) sum[k] += sh[k][s];
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) d.Hll[9 * (size_t)p + k] = sum[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d.gl[3 * (size_t)p + k] = sum[9 + k];
+    }
+  } else {
+    T *smT = &sh[0][0];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const T tot = block_sum<T>(acc[k], smT);
+      if (tid == 0) {
+        if (k < 9) d.Hll[9 * (size_t)pt0 + k] = tot;
+        else d.gl[3 * (size_t)pt0 + (k - 9)] = tot;
+      }
+    }
+  }
+  const double ctot = block_sum<double>(cost, red);
+  if (tid == 0) d.partials[blockIdx.x] = ctot;
+}
+
+// HP1-B: camera-major accumulation of Hpp (upper triangle) and g_c.  One CTA per
+// (camera, chunk of <= CM_CHUNK edges); residual/Jacobian are recomputed from the
+// L2-resident point array instead of being re-read from HBM.
+template <typename T>
+__global__ void __launch_bounds__(CM_THREADS) k_lin_cm(Dev<T> d) {
+  constexpr int NW = CM_THREADS / 32;
+  __shared__ T sh[NW][NTRI + 9];
+  const int4 ch = d.chunk[blockIdx.x];
+  const int c = ch.x, beg = ch.y, end = ch.z;
+  T cm[9];
+  load_cam(d.cam, c, cm);
+  const RotConst<T> rc = rot_const<T>(cm[0], cm[1], cm[2]);
+  T acc[NTRI + 9];
+#pragma unroll
+  for (int k = 0; k < NTRI + 9; ++k) acc[k] = T(0);
+  for (int k = beg + (int)threadIdx.x; k < end; k += CM_THREADS) {
+    const int p = d.cm_pt[k];
+    const T X0 = d.pt[3 * (size_t)p], X1 = d.pt[3 * (size_t)p + 1], X2 = d.pt[3 * (size_t)p + 2];
+    const typename Vec2<T>::type ob = reinterpret_cast<const typename Vec2<T>::type *>(d.cm_obs)[k];
+    T J[24], r0, r1;
+    edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    T Lb[24];
+    const T *L = J;
+    if (d.cm_info) {
+      T om[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) om[q] = d.cm_info[4 * (size_t)k + q];
+      left_factor<T>(J, om, Lb);
+      L = Lb;
+    }
+    int idx = 0;
+#pragma unroll
+    for (int y = 0; y < 9; ++y) {
+#pragma unroll
+      for (int i = y; i < 9; ++i) acc[idx++] += L[y] * J[i] + L[12 + y] * J[12 + i];
+      acc[NTRI + y] -= L[y] * r0 + L[12 + y] * r1;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NTRI + 9; ++k) {
+    const T v = warp_sum<T>(acc[k]);
+    if (lane == 0) sh[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NTRI + 9) {
+    T v = T(0);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += sh[w][threadIdx.x];
+    d.cm_part[(size_t)blockIdx.x * (NTRI + 9) + threadIdx.x] = v;
+  }
+}
+
+// Sum the chunk partials of one camera (fixed order) and expand the triangle.
+template <typename T>
+__global__ void __launch_bounds__(64) k_lin_cam_reduce(Dev<T> d) {
+  const int c = blockIdx.x, k = threadIdx.x;
+  if (k >= NTRI + 9) return;
+  T v = T(0);
+  for (int ch = d.cam_chunk_ptr[c]; ch < d.cam_chunk_ptr[c + 1]; ++ch) v += d.cm_part[(size_t)ch * (NTRI + 9) + k];
+  if (k >= NTRI) {
+    d.gc[9 * (size_t)c + (k - NTRI)] = v;
+  } else {
+    int y = 0, rem = k;
+    while (rem >= 9 - y) { rem -= 9 - y; ++y; }
+    const int i = y + rem;
+    d.Hpp[81 * (size_t)c + 9 * y + i] = v;
+    d.Hpp[81 * (size_t)c + 9 * i + y] = v;
+  }
+}
+
+// Deterministic final reduction of per-CTA partials: out[j] = op_i part[i*ncomp + j].
+template <int OP>  // 0 sum, 1 max
+__global__ void __launch_bounds__(1024) k_reduce(const double *__restrict__ part, int n, int ncomp, double *out) {
+  __shared__ double sm[32];
+  for (int j = 0; j < ncomp; ++j) {
+    double v = 0.;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double x = part[(size_t)i * ncomp + j];
+      v = OP == 0 ? v + x : fmax(v, x);
+    }
+    if (OP == 0) {
+      v = block_sum<double>(v, sm);
+    } else {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+      __syncthreads();
+      v = (threadIdx.x & 31) < (blockDim.x >> 5) ? sm[threadIdx.x & 31] : 0.;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    if (threadIdx.x == 0) out[j] = v;
+  }
+}
+
+// --------------------------------------------------------------------------------
+// Solve preparation
+template <typename T>
+__global__ void __launch_bounds__(256) k_prep_points(Dev<T> d) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.nPl) return;
+  const T a1 = T(d.damp) + T(1);  // (a + 1) * diag, schur_LM_linear_system.cu:123-124,149
+  T h[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) h[k] = d.Hll[9 * (size_t)p + k];
+  h[0] *= a1; h[4] *= a1; h[8] *= a1;
+  const T c00 = h[4] * h[8] - h[5] * h[7], c01 = h[5] * h[6] - h[3] * h[8], c02 = h[3] * h[7] - h[4] * h[6];
+  const T det = h[0] * c00 + h[1] * c01 + h[2] * c02;
+  const T id = det != T(0) ? T(1) / det : T(0);
+  T inv[9];
+  inv[0] = c00 * id;
+  inv[1] = (h[2] * h[7] - h[1] * h[8]) * id;
+  inv[2] = (h[1] * h[5] - h[2] * h[4]) * id;
+  inv[3] = c01 * id;
+  inv[4] = (h[0] * h[8] - h[2] * h[6]) * id;
+  inv[5] = (h[2] * h[3] - h[0] * h[5]) * id;
+  inv[6] = c02 * id;
+  inv[7] = (h[1] * h[6] - h[0] * h[7]) * id;
+  inv[8] = (h[0] * h[4] - h[1] * h[3]) * id;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) d.HllInv[9 * (size_t)p + k] = inv[k];
+  const T g0 = d.gl[3 * (size_t)p], g1 = d.gl[3 * (size_t)p + 1], g2 = d.gl[3 * (size_t)p + 2];
+#pragma unroll
+  for (int y = 0; y < 3; ++y) d.w[3 * (size_t)p + y] = inv[3 * y] * g0 + inv[3 * y + 1] * g1 + inv[3 * y + 2] * g2;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_prep_cams(Dev<T> d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.nC) return;
+  const T a1 = T(d.damp) + T(1);
+  T A[81];
+#pragma unroll
+  for (int k = 0; k < 81; ++k) A[k] = d.Hpp[81 * (size_t)c + k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) A[10 * k] *= a1;
+#pragma unroll
+  for (int k = 0; k < 81; ++k) d.HppD[81 * (size_t)c + k] = A[k];
+  // in-place Gauss-Jordan (SPD block: no pivoting needed)
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const T piv = A[10 * k] != T(0) ? T(1) / A[10 * k] : T(0);
+#pragma unroll
+    for (int j = 0; j < 9; ++j)
+      if (j != k) A[9 * k + j] *= piv;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      if (i == k) continue;
+      const T f = A[9 * i + k];
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        if (j != k) A[9 * i + j] -= f * A[9 * k + j];
+      A[9 * i + k] = -f * piv;
+    }
+    A[10 * k] = piv;
+  }
+#pragma unroll
+  for (int k = 0; k < 81; ++k) d.HppInv[81 * (size_t)c + k] = A[k];
+}
+
+// --------------------------------------------------------------------------------
+// HP2 edge kernel: for every point j of the tile
+//   t_j = sum_e W_e^T x[cam(e)]            (Hlp x, point-local segmented reduction)
+//   u_j = Hll^-1 t_j | w_j | w_j - Hll^-1 t_j   (FULL | MAKEV | BACKSUB)
+//   s[cam(e)] += W_e u_j                   (Hpl u, scatter by RED.ADD to global)
+// W_e (or J_e) is loaded once and stays in registers between the two halves.
+template <typename T, bool IMPLICIT>
+__device__ __forceinline__ void edge_t(const T *wj, const T *x, T *t) {
+  if (!IMPLICIT) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      T a = T(0);
+#pragma unroll
+      for (int y = 0; y < 9; ++y) a += wj[3 * y + q] * x[y];
+      t[q] = a;
+    }
+  } else {
+    T a0 = T(0), a1 = T(0);
+#pragma unroll
+    for (int y = 0; y < 9; ++y) { a0 += wj[y] * x[y]; a1 += wj[12 + y] * x[y]; }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) t[q] = wj[9 + q] * a0 + wj[21 + q] * a1;
+  }
+}
+
+template <typename T, bool IMPLICIT>
+__device__ __forceinline__ void edge_scatter(const T *wj, const T *u, T *out9) {
+  if (!IMPLICIT) {
+#pragma unroll
+    for (int y = 0; y < 9; ++y) out9[y] = wj[3 * y] * u[0] + wj[3 * y + 1] * u[1] + wj[3 * y + 2] * u[2];
+  } else {
+    const T b0 = wj[9] * u[0] + wj[10] * u[1] + wj[11] * u[2];
+    const T b1 = wj[21] * u[0] + wj[22] * u[1] + wj[23] * u[2];
+#pragma unroll
+    for (int y = 0; y < 9; ++y) out9[y] = wj[y] * b0 + wj[12 + y] * b1;
+  }
+}
+
+template <typename T, bool IMPLICIT, int MODE>
+__global__ void __launch_bounds__(TE) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, int check_active) {
+  constexpr int K = IMPLICIT ? 24 : 27;
+  if (check_active && !d.st->active) return;
+  __shared__ T sh_t[3][TE];
+  __shared__ T sh_u[3][TE];
+  const int4 td = d.tile[blockIdx.x];
+  const int slot0 = td.x, ne = td.y, pt0 = td.z, np = td.w;
+  const int tid = threadIdx.x;
+  if (ne <= TE) {
+    const bool valid = tid < ne;
+    T wj[K];
+    int c = 0, lp = 0;
+    if (valid) {
+      const int slot = slot0 + tid;
+      c = d.e_cam[slot];
+      lp = d.e_lp[slot];
+      const T *src = d.WJ + wj_base<T>(slot, K);
+#pragma unroll
+      for (int k = 0; k < K; ++k) wj[k] = __ldg(src + (size_t)k * TE);
+      if (MODE != SM_MAKEV) {
+        T x[9], t[3];
+#pragma unroll
+        for (int y = 0; y < 9; ++y) x[y] = __ldg(xin + 9 * (size_t)c + y);
+        edge_t<T, IMPLICIT>(wj, x, t);
+        sh_t[0][tid] = t[0]; sh_t[1][tid] = t[1]; sh_t[2][tid] = t[2];
+      }
+    }
+    if (MODE != SM_MAKEV) __syncthreads();
+    if (tid < np) {
+      const int p = pt0 + tid;
+      T u[3];
+      if (MODE != SM_MAKEV) {
+        const int s0 = d.pt_slot[p] - slot0;
+        const int s1 = (tid + 1 < np) ? d.pt_slot[p + 1] - slot0 : ne;
+        T t0 = T(0), t1 = T(0), t2 = T(0);
+        for (int s = s0; s < s1; ++s) { t0 += sh_t[0][s]; t1 += sh_t[1][s]; t2 += sh_t[2][s]; }
+        T hi[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInv + 9 * (size_t)p + k);
+#pragma unroll
+        for (int y = 0; y < 3; ++y) u[y] = hi[3 * y] * t0 + hi[3 * y + 1] * t1 + hi[3 * y + 2] * t2;
+        if (MODE == SM_BACKSUB) {
+#pragma unroll
+          for (int y = 0; y < 3; ++y) d.dxl[3 * (size_t)p + y] = d.w[3 * (size_t)p + y] - u[y];
+        }
+      } else {
+#pragma unroll
+        for (int y = 0; y < 3; ++y) u[y] = d.w[3 * (size_t)p + y];
+      }
+      if (MODE != SM_BACKSUB) { sh_u[0][tid] = u[0]; sh_u[1][tid] = u[1]; sh_u[2][tid] = u[2]; }
+    }
+    if (MODE != SM_BACKSUB) {
+      __syncthreads();
+      if (valid) {
+        const T u[3] = {sh_u[0][lp], sh_u[1][lp], sh_u[2][lp]};
+        T o[9];
+        edge_scatter<T, IMPLICIT>(wj, u, o);
+#pragma unroll
+        for (int y = 0; y < 9; ++y) atomicAdd(sout + 9 * (size_t)c + y, o[y]);
+      }
+    }
+  } else {
+    // a single point with more than TE observations: two passes over its slabs
+    T *smT = &sh_t[0][0];
+    T u[3];
+    if (MODE != SM_MAKEV) {
+      T t[3] = {T(0), T(0), T(0)};
+      for (int i = tid; i < ne; i += TE) {
+        const int slot = slot0 + i;
+        const int c = d.e_cam[slot];
+        const T *src = d.WJ + wj_base<T>(slot, K);
+        T wj[K], x[9], te[3];
+#pragma unroll
+        for (int k = 0; k < K; ++k) wj[k] = __ldg(src + (size_t)k * TE);
+#pragma unroll
+        for (int y = 0; y < 9; ++y) x[y] = __ldg(xin + 9 * (size_t)c + y);
+        edge_t<T, IMPLICIT>(wj, x, te);
+        t[0] += te[0]; t[1] += te[1]; t[2] += te[2];
+      }
+      const T t0 = block_sum<T>(t[0], smT), t1 = block_sum<T>(t[1], smT), t2 = block_sum<T>(t[2], smT);
+      T hi[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInv + 9 * (size_t)pt0 + k);
+#pragma unroll
+      for (int y = 0; y < 3; ++y) u[y] = hi[3 * y] * t0 + hi[3 * y + 1] * t1 + hi[3 * y + 2] * t2;
+      if (MODE == SM_BACKSUB) {
+        if (tid == 0) {
+#pragma unroll
+          for (int y = 0; y < 3; ++y) d.dxl[3 * (size_t)pt0 + y] = d.w[3 * (size_t)pt0 + y] - u[y];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int y = 0; y < 3; ++y) u[y] = d.w[3 * (size_t)pt0 + y];
+    }
+    if (MODE != SM_BACKSUB) {
+      for (int i = tid; i < ne; i += TE) {
+        const int slot = slot0 + i;
+        const int c = d.e_cam[slot];
+        const T *src = d.WJ + wj_base<T>(slot, K);
+        T wj[K], o[9];
+#pragma unroll
+        for (int k = 0; k < K; ++k) wj[k] = __ldg(src + (size_t)k * TE);
+        edge_scatter<T, IMPLICIT>(wj, u, o);
+#pragma unroll
+        for (int y = 0; y < 9; ++y) atomicAdd(sout + 9 * (size_t)c + y, o[y]);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------
+// Camera-space PCG kernel.  One cluster of CL CTAs; cameras are split contiguously
+// over the CTAs; the two dot products are reduced through distributed shared memory.
+constexpr int PCG_CL = 8;
+constexpr int PCG_THREADS = 512;
+
+__device__ __forceinline__ double cluster_sum(double v, double *red_warp, double *slot, cg::cluster_group &cl) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum<double>(v);
+  __syncthreads();
+  if (lane == 0) red_warp[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double x = lane < nw ? red_warp[lane] : 0.;
+    x = warp_sum<double>(x);
+    if (lane == 0) *slot = x;
+  }
+  cl.sync();
+  double tot = 0.;
+  const int n = cl.num_blocks();
+  for (int r = 0; r < n; ++r) tot += *cl.map_shared_rank(slot, r);
+  return tot;
+}
+
+// INIT = 1: r = (g_c - sA) - (HppD x0 - sB); z = M^-1 r; rho; p = z      (:182-258,268-313 at n = 0)
+// INIT = 0: bottom half of iteration n + top half of iteration n+1          (:359-406, :268-313)
+template <typename T, int INIT>
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter, double tol, double refuse) {
+  cg::cluster_group cl = cg::this_cluster();
+  __shared__ double red_warp[32];
+  __shared__ double slots[2];
+  PcgState st;
+  if (INIT) {
+    st.rho = 0.; st.rho_prev = 0.; st.rho_min = INFINITY; st.alpha = 0.; st.pq = 0.;
+    st.tol = tol; st.refuse = refuse; st.n = 0; st.max_iter = max_iter; st.active = 1; st.done = 0; st.refused = 0;
+  } else {
+    st = *d.st;
+    if (!st.active) return;  // uniform over the cluster: st is only written after the last cluster.sync
+  }
+  const int ncta = cl.num_blocks(), rank = cl.block_rank();
+  const int per = (d.nC + ncta - 1) / ncta;
+  const int c0 = min(d.nC, rank * per), c1 = min(d.nC, c0 + per);
+  const int i0 = 9 * c0, i1 = 9 * c1;
+  const int tid = threadIdx.x;
+  T *x = d.dxc;
+  if (INIT) {
+    for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
+      const int c = i / 9, k = i - 9 * c;
+      T a = T(0);
+#pragma unroll
+      for (int j = 0; j < 9; ++j) a += d.HppD[81 * (size_t)c + 9 * k + j] * x[9 * c + j];
+      const T v = d.gc[i] - d.sA[i];            // v = g_c - Hpl w          (:478-493)
+      d.r[i] = v - (a - d.sB[i]);               // r = v - (Hpp x0 - Hpl Hll^-1 Hlp x0)
+    }
+  } else {
+    double acc = 0.;
+    for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
+      const int c = i / 9, k = i - 9 * c;
+      T a = T(0);
+#pragma unroll
+      for (int j = 0; j < 9; ++j) a += d.HppD[81 * (size_t)c + 9 * k + j] * d.p[9 * c + j];
+      const T qi = a - d.sB[i];                 // q = Hpp p - Hpl Hll^-1 Hlp p   (:359-366)
+      d.q[i] = qi;
+      acc += (double)(d.p[i] * qi);
+    }
+    const double pq = cluster_sum(acc, red_warp, &slots[0], cl);
+    const T alpha = (T)(st.rho / pq);           // :385
+    st.alpha = (double)alpha; st.pq = pq;
+    for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
+      const T xi = x[i];
+      d.xbk[i] = xi;                            // :389
+      x[i] = xi + alpha * d.p[i];               // :391
+      d.r[i] = d.r[i] + (-alpha) * d.q[i];      // :400
+    }
+  }
+  __syncthreads();
+  double acc = 0.;
+  for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
+    const int c = i / 9, k = i - 9 * c;
+    T a = T(0);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) a += d.HppInv[81 * (size_t)c + 9 * k + j] * d.r[9 * c + j];
+    d.z[i] = a;                                 // z = M^-1 r              (:273-275)
+    acc += (double)(d.r[i] * a);
+  }
+  const double rho_new = (double)(T)cluster_sum(acc, red_warp, &slots[1], cl);  // rhoN is a T in the reference
+  bool cont = true;
+  if (!INIT) {
+    st.n += 1;                                  // :405
+    st.done = fabs(st.rho) < st.tol;            // :406 (rho of the iteration just finished)
+    cont = !st.done && st.n < st.max_iter;      // :407
+  } else {
+    cont = st.max_iter > 0;
+  }
+  if (cont) {
+    if (rho_new > st.refuse * st.rho_min) {     // :288-295
+      st.refused = 1;
+      cont = false;
+      if (!INIT)
+        for (int i = i0 + tid; i < i1; i += PCG_THREADS) x[i] = d.xbk[i];
+    } else {
+      st.rho_min = fmin(st.rho_min, rho_new);   // :296
+      if (!INIT) {
+        const T beta = (T)(rho_new / st.rho);   // :299
+        for (int i = i0 + tid; i < i1; i += PCG_THREADS) d.p[i] = d.z[i] + beta * d.p[i];
+      } else {
+        for (int i = i0 + tid; i < i1; i += PCG_THREADS) d.p[i] = d.z[i];  // :310
+      }
+      st.rho_prev = st.rho;
+      st.rho = rho_new;
+    }
+  }
+  st.active = cont ? 1 : 0;
+  for (int i = i0 + tid; i < i1; i += PCG_THREADS) d.sB[i] = T(0);  // ready for the next edge pass
+  cl.sync();  // nobody leaves while peers may still read its slots; st is written after every read
+  if (rank == 0 && tid == 0) *d.st = st;
+}
+
+// --------------------------------------------------------------------------------
+// LM scalars
+template <typename T>
+__global__ void __launch_bounds__(TE) k_trial(Dev<T> d) {
+  __shared__ double red[32];
+  const int4 td = d.tile[blockIdx.x];
+  const int slot0 = td.x, ne = td.y, pt0 = td.z;
+  double a_model = 0., a_cost = 0.;
+  for (int i = threadIdx.x; i < ne; i += TE) {
+    const int slot = slot0 + i;
+    const int c = d.e_cam[slot];
+    const int p = pt0 + (int)d.e_lp[slot];
+    T cm[9], dc[9];
+    load_cam(d.cam, c, cm);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dc[k] = d.dxc[9 * (size_t)c + k];
+    const T X0 = d.pt[3 * (size_t)p], X1 = d.pt[3 * (size_t)p + 1], X2 = d.pt[3 * (size_t)p + 2];
+    const T D0 = d.dxl[3 * (size_t)p], D1 = d.dxl[3 * (size_t)p + 1], D2 = d.dxl[3 * (size_t)p + 2];
+    const typename Vec2<T>::type ob = reinterpret_cast<const typename Vec2<T>::type *>(d.e_obs)[slot];
+    T J[24], r0, r1;
+    RotConst<T> rc = rot_const<T>(cm[0], cm[1], cm[2]);
+    edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    T m0 = T(0), m1 = T(0);  // J dx  (JdxpF, lm_algo.cu:61-79)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { m0 += J[k] * dc[k]; m1 += J[12 + k] * dc[k]; }
+    m0 += J[9] * D0 + J[10] * D1 + J[11] * D2;
+    m1 += J[21] * D0 + J[22] * D1 + J[23] * D2;
+    a_model += (double)((m0 + r0) * (m0 + r0)) + (double)((m1 + r1) * (m1 + r1));
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cm[k] += dc[k];  // updateDeltaXTwoVertices, update.cu:14-41
+    rc = rot_const<T>(cm[0], cm[1], cm[2]);
+    T s0, s1;
+    edge_residual<T>(cm, rc, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1);
+    a_cost += (double)(s0 * s0) + (double)(s1 * s1);
+  }
+  const double tc = block_sum<double>(a_cost, red);
+  const double tm = block_sum<double>(a_model, red);
+  if (threadIdx.x == 0) {
+    d.partials[2 * (size_t)blockIdx.x] = tc;
+    d.partials[2 * (size_t)blockIdx.x + 1] = tm;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_norms(Dev<T> d) {
+  __shared__ double red[32];
+  double a[4] = {0., 0., 0., 0.};  // dx_pt^2, x_pt^2, dx_cam^2, x_cam^2
+  const size_t stride = (size_t)gridDim.x * blockDim.x, g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = g; i < 3 * (size_t)d.nPl; i += stride) {
+    a[0] += (double)(d.dxl[i] * d.dxl[i]);
+    a[1] += (double)(d.pt[i] * d.pt[i]);
+  }
+  for (size_t i = g; i < 9 * (size_t)d.nC; i += stride) {
+    a[2] += (double)(d.dxc[i] * d.dxc[i]);
+    a[3] += (double)(d.cam[i] * d.cam[i]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double t = block_sum<double>(a[j], red);
+    if (threadIdx.x == 0) d.partials[4 * (size_t)blockIdx.x + j] = t;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_ginf(Dev<T> d) {
+  __shared__ double red[32];
+  double m = 0.;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = g; i < 3 * (size_t)d.nPl; i += stride) m = fmax(m, fabs((double)d.gl[i]));
+  for (size_t i = g; i < 9 * (size_t)d.nC; i += stride) m = fmax(m, fabs((double)d.gc[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) d.partials[blockIdx.x] = m;
+  }
+}
+
+// x += dx (applyUpdate, schur_LM_linear_system.cu:212-218) and deltaX backup (:188-197)
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply_step(Dev<T> d) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x, g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = g; i < 3 * (size_t)d.nPl; i += stride) {
+    const T v = d.dxl[i];
+    d.pt[i] += v;
+    d.dxl_bk[i] = v;
+  }
+  for (size_t i = g; i < 9 * (size_t)d.nC; i += stride) {
+    const T v = d.dxc[i];
+    d.cam[i] += v;
+    d.dxc_bk[i] = v;
+  }
+}
+
+// debug / parity: r[slot][2], J[slot][24]
+template <typename T>
+__global__ void __launch_bounds__(TE) k_eval_edges(Dev<T> d, T *r_out, T *J_out) {
+  const int4 td = d.tile[blockIdx.x];
+  const int slot0 = td.x, ne = td.y, pt0 = td.z;
+  for (int i = threadIdx.x; i < ne; i += TE) {
+    const int slot = slot0 + i;
+    const int c = d.e_cam[slot];
+    const int p = pt0 + (int)d.e_lp[slot];
+    T cm[9];
+    load_cam(d.cam, c, cm);
+    const T X0 = d.pt[3 * (size_t)p], X1 = d.pt[3 * (size_t)p + 1], X2 = d.pt[3 * (size_t)p + 2];
+    const T o0 = d.e_obs[2 * (size_t)slot], o1 = d.e_obs[2 * (size_t)slot + 1];
+    T J[24], r0, r1;
+    const RotConst<T> rc = rot_const<T>(cm[0], cm[1], cm[2]);
+    edge_residual_jacobian<T>(cm, rc, X0, X1, X2, o0, o1, r0, r1, J);
+    r_out[2 * (size_t)slot] = r0;
+    r_out[2 * (size_t)slot + 1] = r1;
+    if (J_out) {
+#pragma unroll
+      for (int k = 0; k < 24; ++k) J_out[24 * (size_t)slot + k] = J[k];
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cam_matvec_sub(Dev<T> d, const T *p, const T *s, T *q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * d.nC) return;
+  const int c = i / 9, k = i - 9 * c;
+  T a = T(0);
+#pragma unroll
+  for (int j = 0; j < 9; ++j) a += d.HppD[81 * (size_t)c + 9 * k + j] * p[9 * c + j];
+  q[i] = a - s[i];
+}
+
+// --------------------------------------------------------------------------------
+// launchers
+template <typename T>
+cudaError_t launch_linearize(const Dev<T> &d, cudaStream_t st) {
+  if (d.nT > 0) {
+    if (d.implicit) k_lin_pm<T, true><<<d.nT, TE, 0, st>>>(d);
+    else k_lin_pm<T, false><<<d.nT, TE, 0, st>>>(d);
+  }
+  if (d.nChunks > 0) k_lin_cm<T><<<d.nChunks, CM_THREADS, 0, st>>>(d);
+  k_lin_cam_reduce<T><<<d.nC, 64, 0, st>>>(d);
+  k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nT, 1, d.scal + S_COST);
+  return cudaGetLastError();
+}
+int launches_of_linearize() { return 4; }
+
+template <typename T>
+cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st) {
+  if (d.nPl > 0) k_prep_points<T><<<(d.nPl + 255) / 256, 256, 0, st>>>(d);
+  k_prep_cams<T><<<(d.nC + 63) / 64, 64, 0, st>>>(d);
+  return cudaGetLastError();
+}
+int launches_of_prep() { return 2; }
+
+template <typename T, bool IMPLICIT>
+static void launch_schur_edge_t(const Dev<T> &d, int mode, const T *xin, T *sout, int check_active, cudaStream_t st) {
+  switch (mode) {
+    case SM_FULL: k_schur_edge<T, IMPLICIT, SM_FULL><<<d.nT, TE, 0, st>>>(d, xin, sout, check_active); break;
+    case SM_MAKEV: k_schur_edge<T, IMPLICIT, SM_MAKEV><<<d.nT, TE, 0, st>>>(d, xin, sout, check_active); break;
+    default: k_schur_edge<T, IMPLICIT, SM_BACKSUB><<<d.nT, TE, 0, st>>>(d, xin, sout, check_active); break;
+  }
+}
+
+template <typename T>
+cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, int check_active, cudaStream_t st) {
+  if (d.nT == 0) return cudaSuccess;
+  if (d.implicit) launch_schur_edge_t<T, true>(d, mode, xin, sout, check_active, st);
+  else launch_schur_edge_t<T, false>(d, mode, xin, sout, check_active, st);
+  return cudaGetLastError();
+}
+
+template <typename T, int INIT>
+static cudaError_t launch_pcg_cam(const Dev<T> &d, int max_iter, double tol, double refuse, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PCG_CL);
+  cfg.blockDim = dim3(PCG_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PCG_CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_pcg_cam<T, INIT>, d, max_iter, tol, refuse);
+}
+
+template <typename T>
+cudaError_t launch_pcg_init(const Dev<T> &d, int max_iter, double tol, double refuse, cudaStream_t st) {
+  return launch_pcg_cam<T, 1>(d, max_iter, tol, refuse, st);
+}
+template <typename T>
+cudaError_t launch_pcg_step(const Dev<T> &d, cudaStream_t st) {
+  return launch_pcg_cam<T, 0>(d, 0, 0., 0., st);
+}
+
+template <typename T>
+cudaError_t launch_trial(const Dev<T> &d, cudaStream_t st) {
+  if (d.nT > 0) k_trial<T><<<d.nT, TE, 0, st>>>(d);
+  k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nT, 2, d.scal + S_TRIAL_COST);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_norms(const Dev<T> &d, cudaStream_t st) {
+  k_norms<T><<<AUX_GRID, 256, 0, st>>>(d);
+  k_reduce<0><<<1, 1024, 0, st>>>(d.partials, AUX_GRID, 4, d.scal + S_DX2_PT);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_apply_step(const Dev<T> &d, cudaStream_t st) {
+  k_apply_step<T><<<AUX_GRID, 256, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_ginf(const Dev<T> &d, cudaStream_t st) {
+  k_ginf<T><<<AUX_GRID, 256, 0, st>>>(d);
+  k_reduce<1><<<1, 1024, 0, st>>>(d.partials, AUX_GRID, 1, d.scal + S_GINF);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_eval_edges(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st) {
+  if (d.nT > 0) k_eval_edges<T><<<d.nT, TE, 0, st>>>(d, r_slots, J_slots);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_cam_matvec_sub(const Dev<T> &d, const T *p, const T *s, T *q, cudaStream_t st) {
+  k_cam_matvec_sub<T><<<(9 * d.nC + 255) / 256, 256, 0, st>>>(d, p, s, q);
+  return cudaGetLastError();
+}
+
+#define BA_INSTANTIATE(T)                                                                                   \
+  template cudaError_t launch_linearize<T>(const Dev<T> &, cudaStream_t);                                   \
+  template cudaError_t launch_schur_edge<T>(const Dev<T> &, int, const T *, T *, int, cudaStream_t);        \
+  template cudaError_t launch_prep<T>(const Dev<T> &, cudaStream_t);                                        \
+  template cudaError_t launch_pcg_init<T>(const Dev<T> &, int, double, double, cudaStream_t);               \
+  template cudaError_t launch_pcg_step<T>(const Dev<T> &, cudaStream_t);                                    \
+  template cudaError_t launch_trial<T>(const Dev<T> &, cudaStream_t);                                       \
+  template cudaError_t launch_norms<T>(const Dev<T> &, cudaStream_t);                                       \
+  template cudaError_t launch_apply_step<T>(const Dev<T> &, cudaStream_t);                                  \
+  template cudaError_t launch_ginf<T>(const Dev<T> &, cudaStream_t);                                        \
+  template cudaError_t launch_eval_edges<T>(const Dev<T> &, T *, T *, cudaStream_t);                        \
+  template cudaError_t launch_cam_matvec_sub<T>(const Dev<T> &, const T *, const T *, T *, cudaStream_t);
+BA_INSTANTIATE(double)
+BA_INSTANTIATE(float)
+
+}  // namespace ba
