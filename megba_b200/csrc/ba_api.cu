@@ -326,7 +326,7 @@ struct ImplT : Impl {
     add(&d.cm_part, (size_t)g.nChunks * 54);
     add(&d.HppD, 81 * nC); add(&d.HppInv, 81 * nC); add(&d.HllInv, 9 * nPl); add(&d.w, 3 * nPl);
     add(&d.dxc, 9 * nC); add(&d.dxl, 3 * nPl); add(&d.dxc_bk, 9 * nC); add(&d.dxl_bk, 3 * nPl);
-    add(&d.sA, 18 * nC);  // sA followed by sB
+    add(&d.sA, 2 * (size_t)NREP * 9 * nC);  // sA[NREP][9nC] followed by sB[NREP][9nC]
     add(&d.r, 9 * nC); add(&d.p, 9 * nC); add(&d.q, 9 * nC); add(&d.z, 9 * nC); add(&d.xbk, 9 * nC);
     add(&d.st, 1); add(&d.scal, S_COUNT); add(&d.partials, nPart);
     size_t total = 0;
@@ -340,7 +340,7 @@ struct ImplT : Impl {
       off += (it.bytes + 255) / 256 * 256 + 256;
     }
     d.gc = d.Hpp + 81 * nC;
-    d.sB = d.sA + 9 * nC;
+    d.sB = d.sA + (size_t)NREP * 9 * nC;
     d.nC = (int)nC; d.nPl = (int)nPl; d.nT = g.nT; d.nSlabs = g.nSlabs; d.nChunks = g.nChunks; d.nEl = g.nEl;
     d.implicit = opt.compute_kind == BA_IMPLICIT;
     d.tile = tile; d.e_cam = e_cam; d.e_lp = e_lp; d.e_obs = e_obs; d.e_info = nullptr; d.pt_slot = pt_slot;
@@ -496,13 +496,20 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     size_t ev_s = 0, ev_p = 0;
     if (timing) ev_s = ev_begin();
-    BA_CUDA(cudaMemsetAsync(d.sA, 0, sizeof(T) * 18 * g.nC, stream));
+    const bool multi = opt.world_size > 1;
+    const int nrep = multi ? 1 : NREP;  // multi-GPU: replicas are folded before the allreduce
+    BA_CUDA(cudaMemsetAsync(d.sA, 0, sizeof(T) * 2 * NREP * 9 * g.nC, stream));
     BA_CUDA(launch_prep<T>(d, stream));
     stats.launches += launches_of_prep();
     BA_TRY(schur_edge(SM_MAKEV, nullptr, d.sA, 0, false));  // sA = Hpl w
     BA_TRY(schur_edge(SM_FULL, d.dxc, d.sB, 0, true));      // sB = Hpl Hll^-1 Hlp x0
-    BA_TRY(allreduce_T(d.sA, 18 * (size_t)g.nC));
-    BA_CUDA(launch_pcg_init<T>(d, o->max_iter, o->tol, o->refuse_ratio, stream));
+    if (multi) {
+      BA_CUDA(launch_fold_replicas<T>(d, d.sA, 2, stream));
+      stats.launches += 1;
+      BA_TRY(allreduce_T(d.sA, 9 * (size_t)g.nC));
+      BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
+    }
+    BA_CUDA(launch_pcg_init<T>(d, o->max_iter, o->tol, o->refuse_ratio, nrep, stream));
     stats.launches += 1;
     if (timing) ev_p = ev_begin();
     int launched = 0, n_seen = 0;
@@ -511,8 +518,12 @@ struct ImplT : Impl {
       const size_t ev_mark = ev_schur.size();
       for (int i = 0; i < n; ++i) {
         BA_TRY(schur_edge(SM_FULL, d.p, d.sB, 1, true));
-        BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
-        BA_CUDA(launch_pcg_step<T>(d, stream));
+        if (multi) {
+          BA_CUDA(launch_fold_replicas<T>(d, d.sB, 1, stream));
+          stats.launches += 1;
+          BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
+        }
+        BA_CUDA(launch_pcg_step<T>(d, nrep, stream));
         stats.launches += 1;
       }
       launched += n;
@@ -683,14 +694,15 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     BA_CUDA(launch_prep<T>(d, stream));
     stats.launches += launches_of_prep();
-    BA_CUDA(cudaMemsetAsync(d.sB, 0, sizeof(T) * 9 * g.nC, stream));
+    BA_CUDA(cudaMemsetAsync(d.sB, 0, sizeof(T) * NREP * 9 * g.nC, stream));
     BA_CUDA(cudaMemcpyAsync(d.z, p_v, sizeof(T) * 9 * g.nC, cudaMemcpyHostToDevice, stream));
     BA_TRY(schur_edge(SM_FULL, d.z, d.sB, 0, true));
+    BA_CUDA(launch_fold_replicas<T>(d, d.sB, 1, stream));
     BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
     BA_CUDA(launch_cam_matvec_sub<T>(d, d.z, d.sB, d.q, stream));
-    stats.launches += 1;
+    stats.launches += 2;
     BA_CUDA(cudaMemcpyAsync(q_v, d.q, sizeof(T) * 9 * g.nC, cudaMemcpyDeviceToHost, stream));
-    BA_CUDA(cudaMemsetAsync(d.sB, 0, sizeof(T) * 9 * g.nC, stream));
+    BA_CUDA(cudaMemsetAsync(d.sB, 0, sizeof(T) * NREP * 9 * g.nC, stream));
     BA_CUDA(cudaStreamSynchronize(stream));
     return BA_OK;
   }

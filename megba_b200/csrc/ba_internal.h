@@ -21,6 +21,7 @@ constexpr int TE = 256;       // slots per slab == threads of the edge kernels
 constexpr int CM_CHUNK = 1024;  // edges per camera-major work item
 constexpr int CM_THREADS = 128;
 constexpr int NTRI = 45;       // upper triangle of a 9x9 block
+constexpr int NREP = 16;        // replicas of the camera-space scatter target (spreads REDs over L2 slices)
 constexpr int AUX_GRID = 296;   // 2 CTAs per SM for the small grid-stride kernels
 
 struct PcgState {
@@ -64,7 +65,7 @@ struct Dev {
   T *HllInv, *w;                // [nPl][9], [nPl][3]
   T *dxc, *dxl;                 // step: [9nC], [3nPl]
   T *dxc_bk, *dxl_bk;           // LM backup of the step (warm start after a reject)
-  T *sA, *sB;                   // [9nC] each, contiguous: edge-kernel scatter targets
+  T *sA, *sB;                   // [NREP][9nC] each, contiguous: edge-kernel scatter targets (replicated)
   T *r, *p, *q, *z, *xbk;       // PCG vectors [9nC]
   PcgState *st;
   double *scal;                 // [S_COUNT]
@@ -78,8 +79,10 @@ enum SchurMode { SM_FULL = 0, SM_MAKEV = 1, SM_BACKSUB = 2 };
 template <typename T> cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, int check_active,
                                                     cudaStream_t st);
 template <typename T> cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st);
-template <typename T> cudaError_t launch_pcg_init(const Dev<T> &d, int max_iter, double tol, double refuse, cudaStream_t st);
-template <typename T> cudaError_t launch_pcg_step(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_pcg_init(const Dev<T> &d, int max_iter, double tol, double refuse, int nrep, cudaStream_t st);
+template <typename T> cudaError_t launch_pcg_step(const Dev<T> &d, int nrep, cudaStream_t st);
+template <typename T> cudaError_t launch_fold_replicas(const Dev<T> &d, T *s, int nvec, cudaStream_t st);
+int pcg_cluster_size();
 template <typename T> cudaError_t launch_trial(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_norms(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_apply_step(const Dev<T> &d, cudaStream_t st);

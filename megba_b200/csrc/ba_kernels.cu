@@ -376,15 +376,40 @@ __device__ __forceinline__ void edge_scatter(const T *wj, const T *u, T *out9) {
   }
 }
 
+// Camera-side scatter of one warp's 32 x 9 values.  The values are staged through shared memory so
+// that consecutive lanes add consecutive components of one camera (3 RED sectors per observation
+// instead of 9), and the target vector exists in NREP replicas selected by CTA so the RED traffic is
+// spread over all L2 slices (profiles/r01_microbench_red.txt: 0.47 ms -> 0.087 ms for Venice).
+template <typename T>
+__device__ __forceinline__ void warp_scatter9(T *sv, int *sc, const T *o, int c, T *dst) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T *mine = sv + (size_t)w * 32 * 9;
+  int *cams = sc + w * 32;
+  cams[lane] = c;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) mine[lane * 9 + k] = o[k];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int v = j * 32 + lane, el = v / 9, k = v - 9 * el;
+    const int cc = cams[el];
+    if (cc >= 0) atomicAdd(dst + 9 * (size_t)cc + k, mine[v]);
+  }
+  __syncwarp();
+}
+
 template <typename T, bool IMPLICIT, int MODE>
 __global__ void __launch_bounds__(TE) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, int check_active) {
   constexpr int K = IMPLICIT ? 24 : 27;
   if (check_active && !d.st->active) return;
   __shared__ T sh_t[3][TE];
   __shared__ T sh_u[3][TE];
+  __shared__ T sv[MODE != SM_BACKSUB ? TE * 9 : 1];
+  __shared__ int sc[MODE != SM_BACKSUB ? TE : 1];
   const int4 td = d.tile[blockIdx.x];
   const int slot0 = td.x, ne = td.y, pt0 = td.z, np = td.w;
   const int tid = threadIdx.x;
+  T *dst = MODE != SM_BACKSUB ? sout + (size_t)(blockIdx.x % NREP) * (9 * (size_t)d.nC) : nullptr;
   if (ne <= TE) {
     const bool valid = tid < ne;
     T wj[K];
@@ -430,13 +455,12 @@ __global__ void __launch_bounds__(TE) k_schur_edge(Dev<T> d, const T *__restrict
     }
     if (MODE != SM_BACKSUB) {
       __syncthreads();
+      T o[9];
       if (valid) {
         const T u[3] = {sh_u[0][lp], sh_u[1][lp], sh_u[2][lp]};
-        T o[9];
         edge_scatter<T, IMPLICIT>(wj, u, o);
-#pragma unroll
-        for (int y = 0; y < 9; ++y) atomicAdd(sout + 9 * (size_t)c + y, o[y]);
       }
+      warp_scatter9<T>(sv, sc, o, valid ? c : -1, dst);
     }
   } else {
     // a single point with more than TE observations: two passes over its slabs
@@ -473,16 +497,20 @@ __global__ void __launch_bounds__(TE) k_schur_edge(Dev<T> d, const T *__restrict
       for (int y = 0; y < 3; ++y) u[y] = d.w[3 * (size_t)pt0 + y];
     }
     if (MODE != SM_BACKSUB) {
-      for (int i = tid; i < ne; i += TE) {
-        const int slot = slot0 + i;
-        const int c = d.e_cam[slot];
-        const T *src = d.WJ + wj_base<T>(slot, K);
-        T wj[K], o[9];
+      for (int base = 0; base < ne; base += TE) {
+        const int i = base + tid;
+        int c = -1;
+        T o[9];
+        if (i < ne) {
+          const int slot = slot0 + i;
+          c = d.e_cam[slot];
+          const T *src = d.WJ + wj_base<T>(slot, K);
+          T wj[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) wj[k] = __ldg(src + (size_t)k * TE);
-        edge_scatter<T, IMPLICIT>(wj, u, o);
-#pragma unroll
-        for (int y = 0; y < 9; ++y) atomicAdd(sout + 9 * (size_t)c + y, o[y]);
+          for (int k = 0; k < K; ++k) wj[k] = __ldg(src + (size_t)k * TE);
+          edge_scatter<T, IMPLICIT>(wj, u, o);
+        }
+        warp_scatter9<T>(sv, sc, o, c, dst);
       }
     }
   }
@@ -515,7 +543,7 @@ __device__ __forceinline__ double cluster_sum(double v, double *red_warp, double
 // INIT = 1: r = (g_c - sA) - (HppD x0 - sB); z = M^-1 r; rho; p = z      (:182-258,268-313 at n = 0)
 // INIT = 0: bottom half of iteration n + top half of iteration n+1          (:359-406, :268-313)
 template <typename T, int INIT>
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter, double tol, double refuse) {
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter, double tol, double refuse, int nrep) {
   cg::cluster_group cl = cg::this_cluster();
   __shared__ double red_warp[32];
   __shared__ double slots[2];
@@ -532,7 +560,20 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter,
   const int c0 = min(d.nC, rank * per), c1 = min(d.nC, c0 + per);
   const int i0 = 9 * c0, i1 = 9 * c1;
   const int tid = threadIdx.x;
+  const size_t rs = 9 * (size_t)d.nC;
   T *x = d.dxc;
+  // fold the replicas of the scatter targets into replica 0 (own rows only)
+  for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
+    T a = d.sB[i];
+    for (int rep = 1; rep < nrep; ++rep) a += d.sB[rep * rs + i];
+    d.sB[i] = a;
+    if (INIT) {
+      T b = d.sA[i];
+      for (int rep = 1; rep < nrep; ++rep) b += d.sA[rep * rs + i];
+      d.sA[i] = b;
+    }
+  }
+  __syncthreads();
   if (INIT) {
     for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
       const int c = i / 9, k = i - 9 * c;
@@ -601,9 +642,170 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter,
     }
   }
   st.active = cont ? 1 : 0;
-  for (int i = i0 + tid; i < i1; i += PCG_THREADS) d.sB[i] = T(0);  // ready for the next edge pass
+  for (int rep = 0; rep < nrep; ++rep)
+    for (int i = i0 + tid; i < i1; i += PCG_THREADS) d.sB[rep * rs + i] = T(0);  // ready for the next edge pass
   cl.sync();  // nobody leaves while peers may still read its slots; st is written after every read
   if (rank == 0 && tid == 0) *d.st = st;
+}
+
+// Register-resident variant (the one normally used): every thread owns RPT rows of the camera-space
+// vectors and keeps their Hpp / Hpp^-1 rows, p, r, x in registers for the whole kernel, so the kernel
+// is one L2 round trip + two cluster reductions instead of a chain of dependent global round trips.
+template <typename T, int INIT, int RPT, bool PRE_INV>
+__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int max_iter, double tol, double refuse, int nrep) {
+  cg::cluster_group cl = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double red_warp[32];
+  __shared__ double slots[2];
+  PcgState st;
+  if (INIT) {
+    st.rho = 0.; st.rho_prev = 0.; st.rho_min = INFINITY; st.alpha = 0.; st.pq = 0.;
+    st.tol = tol; st.refuse = refuse; st.n = 0; st.max_iter = max_iter; st.active = 1; st.done = 0; st.refused = 0;
+  } else {
+    st = *d.st;
+    if (!st.active) return;
+  }
+  const int ncta = cl.num_blocks(), rank = cl.block_rank();
+  const int per = (d.nC + ncta - 1) / ncta;
+  const int c0 = min(d.nC, rank * per), c1 = min(d.nC, c0 + per);
+  const int i0 = 9 * c0, nrows = 9 * (c1 - c0);
+  const int tid = threadIdx.x;
+  const size_t rs = 9 * (size_t)d.nC;
+  T *p_s = reinterpret_cast<T *>(smraw);
+  T *r_s = p_s + RPT * PCG_THREADS;
+  T hd[RPT][9], hi[PRE_INV ? RPT : 1][9], pj[RPT], rj[RPT], xj[RPT], xb[RPT], sj[RPT], qj[RPT], zj[RPT];
+  // ---- one wave of independent loads
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int l = tid + j * PCG_THREADS;
+    pj[j] = rj[j] = xj[j] = xb[j] = sj[j] = qj[j] = zj[j] = T(0);
+    if (l < nrows) {
+      const int i = i0 + l, c = i / 9, k = i - 9 * c;
+#pragma unroll
+      for (int m = 0; m < 9; ++m) hd[j][m] = __ldg(d.HppD + 81 * (size_t)c + 9 * k + m);
+      if (PRE_INV) {
+#pragma unroll
+        for (int m = 0; m < 9; ++m) hi[j][m] = __ldg(d.HppInv + 81 * (size_t)c + 9 * k + m);
+      }
+      xj[j] = d.dxc[i];
+      T sb = T(0);
+      for (int rep = 0; rep < nrep; ++rep) sb += d.sB[rep * rs + i];
+      sj[j] = sb;
+      if (INIT) {
+        T sa = T(0);
+        for (int rep = 0; rep < nrep; ++rep) sa += d.sA[rep * rs + i];
+        pj[j] = xj[j];               // operand of Hpp x0
+        rj[j] = d.gc[i] - sa;        // v = g_c - Hpl w                      (:478-493)
+      } else {
+        pj[j] = d.p[i];
+        rj[j] = d.r[i];
+      }
+      p_s[l] = pj[j];
+    }
+  }
+  __syncthreads();
+  double acc = 0.;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int l = tid + j * PCG_THREADS;
+    if (l < nrows) {
+      const int lc = l - (i0 + l) % 9;
+      T a = T(0);
+#pragma unroll
+      for (int m = 0; m < 9; ++m) a += hd[j][m] * p_s[lc + m];
+      qj[j] = a - sj[j];                       // q = Hpp p - Hpl Hll^-1 Hlp p  (:359-366)
+      if (INIT) rj[j] = rj[j] - qj[j];         // r = v - S x0                  (:182-258)
+      else acc += (double)(pj[j] * qj[j]);
+    }
+  }
+  if (!INIT) {
+    const double pq = cluster_sum(acc, red_warp, &slots[0], cl);
+    const T alpha = (T)(st.rho / pq);          // :385
+    st.alpha = (double)alpha; st.pq = pq;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      xb[j] = xj[j];                           // :389
+      xj[j] = xj[j] + alpha * pj[j];           // :391
+      rj[j] = rj[j] + (-alpha) * qj[j];        // :400
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int l = tid + j * PCG_THREADS;
+    if (l < nrows) r_s[l] = rj[j];
+  }
+  __syncthreads();
+  acc = 0.;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int l = tid + j * PCG_THREADS;
+    if (l < nrows) {
+      const int i = i0 + l, c = i / 9, k = i - 9 * c, lc = l - k;
+      T a = T(0);
+#pragma unroll
+      for (int m = 0; m < 9; ++m) {
+        const T h = PRE_INV ? hi[j][m] : __ldg(d.HppInv + 81 * (size_t)c + 9 * k + m);
+        a += h * r_s[lc + m];
+      }
+      zj[j] = a;                               // z = M^-1 r                    (:273-275)
+      acc += (double)(rj[j] * a);
+    }
+  }
+  const double rho_new = (double)(T)cluster_sum(acc, red_warp, &slots[1], cl);
+  bool cont = true, refused = false;
+  if (!INIT) {
+    st.n += 1;                                 // :405
+    st.done = fabs(st.rho) < st.tol;           // :406
+    cont = !st.done && st.n < st.max_iter;     // :407
+  } else {
+    cont = st.max_iter > 0;
+  }
+  T beta = T(0);
+  if (cont) {
+    if (rho_new > st.refuse * st.rho_min) {    // :288-295
+      st.refused = 1;
+      refused = true;
+      cont = false;
+    } else {
+      st.rho_min = fmin(st.rho_min, rho_new);  // :296
+      if (!INIT) beta = (T)(rho_new / st.rho); // :299
+      st.rho_prev = st.rho;
+      st.rho = rho_new;
+    }
+  }
+  st.active = cont ? 1 : 0;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int l = tid + j * PCG_THREADS;
+    if (l < nrows) {
+      const int i = i0 + l;
+      d.r[i] = rj[j];
+      if (!INIT) {
+        d.dxc[i] = refused ? xb[j] : xj[j];
+        d.xbk[i] = xb[j];
+      }
+      if (cont) d.p[i] = INIT ? zj[j] : zj[j] + beta * pj[j];  // :310 / :299-306
+      for (int rep = 0; rep < nrep; ++rep) d.sB[rep * rs + i] = T(0);
+    }
+  }
+  cl.sync();
+  if (rank == 0 && tid == 0) *d.st = st;
+}
+
+// s[0][i] += sum_{r>=1} s[r][i]; replicas r >= 1 are cleared.  Used before an NCCL allreduce.
+template <typename T>
+__global__ void __launch_bounds__(256) k_fold_replicas(T *s, int n, int nvec, size_t vec_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int v = 0; v < nvec; ++v) {
+    T *b = s + v * vec_stride;
+    T a = b[i];
+    for (int rep = 1; rep < NREP; ++rep) {
+      a += b[(size_t)rep * n + i];
+      b[(size_t)rep * n + i] = T(0);
+    }
+    b[i] = a;
+  }
 }
 
 // --------------------------------------------------------------------------------
@@ -780,30 +982,89 @@ cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, 
   return cudaGetLastError();
 }
 
-template <typename T, int INIT>
-static cudaError_t launch_pcg_cam(const Dev<T> &d, int max_iter, double tol, double refuse, cudaStream_t st) {
+template <typename K, typename T>
+static cudaError_t launch_cluster(K kernel, int cl, size_t smem, const Dev<T> &d, int max_iter, double tol, double refuse,
+                                  int nrep, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(PCG_CL);
+  cfg.gridDim = dim3(cl);
   cfg.blockDim = dim3(PCG_THREADS);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PCG_CL;
+  attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_pcg_cam<T, INIT>, d, max_iter, tol, refuse);
+  return cudaLaunchKernelEx(&cfg, kernel, d, max_iter, tol, refuse, nrep);
+}
+
+template <typename T, int INIT, int RPT>
+static cudaError_t launch_pcg_reg(const Dev<T> &d, int cl, int max_iter, double tol, double refuse, int nrep,
+                                  cudaStream_t st) {
+  constexpr bool PRE = RPT <= 1 || sizeof(T) == 4;
+  auto kern = k_pcg_cam_reg<T, INIT, RPT, PRE>;
+  const size_t smem = 2 * (size_t)RPT * PCG_THREADS * sizeof(T);
+  static bool prepared = false;  // per instantiation
+  if (!prepared) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prepared = true;
+  }
+  return launch_cluster(kern, cl, smem, d, max_iter, tol, refuse, nrep, st);
+}
+
+// 16-CTA clusters are "non-portable": ask the occupancy API once whether this device can host one.
+int pcg_cluster_size() {
+  static int cached = 0;
+  if (cached) return cached;
+  auto kern = k_pcg_cam_reg<double, 0, 2, false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(16);
+  cfg.blockDim = dim3(PCG_THREADS);
+  cfg.dynamicSmemBytes = 2 * 2 * PCG_THREADS * sizeof(double);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 16;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  if (e != cudaSuccess) cudaGetLastError();
+  cached = (e == cudaSuccess && n >= 1) ? 16 : PCG_CL;
+  return cached;
+}
+
+template <typename T, int INIT>
+static cudaError_t launch_pcg_cam(const Dev<T> &d, int max_iter, double tol, double refuse, int nrep, cudaStream_t st) {
+  const int cl = pcg_cluster_size();
+  const int rows = 9 * ((d.nC + cl - 1) / cl);
+  const int rpt = (rows + PCG_THREADS - 1) / PCG_THREADS;
+  if (rpt <= 1) return launch_pcg_reg<T, INIT, 1>(d, cl, max_iter, tol, refuse, nrep, st);
+  if (rpt <= 2) return launch_pcg_reg<T, INIT, 2>(d, cl, max_iter, tol, refuse, nrep, st);
+  if (rpt <= 4) return launch_pcg_reg<T, INIT, 4>(d, cl, max_iter, tol, refuse, nrep, st);
+  if (rpt <= 8) return launch_pcg_reg<T, INIT, 8>(d, cl, max_iter, tol, refuse, nrep, st);
+  return launch_cluster(k_pcg_cam<T, INIT>, PCG_CL, 0, d, max_iter, tol, refuse, nrep, st);
 }
 
 template <typename T>
-cudaError_t launch_pcg_init(const Dev<T> &d, int max_iter, double tol, double refuse, cudaStream_t st) {
-  return launch_pcg_cam<T, 1>(d, max_iter, tol, refuse, st);
+cudaError_t launch_pcg_init(const Dev<T> &d, int max_iter, double tol, double refuse, int nrep, cudaStream_t st) {
+  return launch_pcg_cam<T, 1>(d, max_iter, tol, refuse, nrep, st);
 }
 template <typename T>
-cudaError_t launch_pcg_step(const Dev<T> &d, cudaStream_t st) {
-  return launch_pcg_cam<T, 0>(d, 0, 0., 0., st);
+cudaError_t launch_pcg_step(const Dev<T> &d, int nrep, cudaStream_t st) {
+  return launch_pcg_cam<T, 0>(d, 0, 0., 0., nrep, st);
+}
+
+template <typename T>
+cudaError_t launch_fold_replicas(const Dev<T> &d, T *s, int nvec, cudaStream_t st) {
+  const int n = 9 * d.nC;
+  k_fold_replicas<T><<<(n + 255) / 256, 256, 0, st>>>(s, n, nvec, (size_t)NREP * n);
+  return cudaGetLastError();
 }
 
 template <typename T>
@@ -849,8 +1110,9 @@ cudaError_t launch_cam_matvec_sub(const Dev<T> &d, const T *p, const T *s, T *q,
   template cudaError_t launch_linearize<T>(const Dev<T> &, cudaStream_t);                                   \
   template cudaError_t launch_schur_edge<T>(const Dev<T> &, int, const T *, T *, int, cudaStream_t);        \
   template cudaError_t launch_prep<T>(const Dev<T> &, cudaStream_t);                                        \
-  template cudaError_t launch_pcg_init<T>(const Dev<T> &, int, double, double, cudaStream_t);               \
-  template cudaError_t launch_pcg_step<T>(const Dev<T> &, cudaStream_t);                                    \
+  template cudaError_t launch_pcg_init<T>(const Dev<T> &, int, double, double, int, cudaStream_t);          \
+  template cudaError_t launch_pcg_step<T>(const Dev<T> &, int, cudaStream_t);                               \
+  template cudaError_t launch_fold_replicas<T>(const Dev<T> &, T *, int, cudaStream_t);                     \
   template cudaError_t launch_trial<T>(const Dev<T> &, cudaStream_t);                                       \
   template cudaError_t launch_norms<T>(const Dev<T> &, cudaStream_t);                                       \
   template cudaError_t launch_apply_step<T>(const Dev<T> &, cudaStream_t);                                  \
