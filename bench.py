@@ -250,6 +250,7 @@ def run_ours(args, P, dtype):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": a_pcg,
                 "avg_launch_ms": k_ms, "launches_timed": st["schur_apply_calls"],
+                "pcg_cam_kernel_avg_ms": st["pcg_cam_ms"] / max(st["pcg_iters"], 1),
                 "linearize": {"algorithmic_bytes": a_lin,
                               "avg_ms": st["linearize_ms"] / max(st["linearize_calls"], 1),
                               "achieved": a_lin / (st["linearize_ms"] / max(st["linearize_calls"], 1) * 1e-3) / 1e9}}

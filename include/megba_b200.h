@@ -93,7 +93,8 @@ typedef struct {
   double linearize_ms;       /* summed device time of ba_linearize (timing on)   */
   double pcg_loop_ms;        /* device time inside the PCG do-while bodies       */
   double solve_ms;           /* device time of ba_solve (inverse+MakeV+PCG+SolveW)*/
-  double reserved[4];
+  double pcg_cam_ms;         /* summed device time of the camera-space PCG kernel (all launches)   */
+  double reserved[3];
 } ba_stats;
 
 typedef struct ba_solver ba_solver;

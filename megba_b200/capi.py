@@ -54,7 +54,8 @@ class Stats(C.Structure):
     _fields_ = [("launches", C.c_int64), ("lm_iters", C.c_int64), ("pcg_iters", C.c_int64),
                 ("schur_apply_calls", C.c_int64), ("schur_apply_ms", C.c_double),
                 ("linearize_calls", C.c_int64), ("linearize_ms", C.c_double),
-                ("pcg_loop_ms", C.c_double), ("solve_ms", C.c_double), ("reserved", C.c_double * 4)]
+                ("pcg_loop_ms", C.c_double), ("solve_ms", C.c_double), ("pcg_cam_ms", C.c_double),
+                ("reserved", C.c_double * 3)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -235,10 +235,11 @@ struct ImplT : Impl {
   T *e_info_dev = nullptr, *cm_info_dev = nullptr;
   T *pt_full = nullptr;  // [3 nP] gather buffer, world_size > 1 only
   double *h_scal = nullptr;
-  PcgState *h_st = nullptr;
+  PcgState *h_st = nullptr;  // two pinned slots (chunk k is polled while chunk k+1 runs)
+  cudaEvent_t st_event[2] = {nullptr, nullptr};
   std::vector<EventPair> ev_pool;
   size_t ev_used = 0;
-  std::vector<size_t> ev_schur, ev_lin, ev_pcg, ev_solve;
+  std::vector<size_t> ev_schur, ev_lin, ev_pcg, ev_solve, ev_cam;
   int pcg_chunk = 8;
 
   ~ImplT() override {
@@ -250,6 +251,7 @@ struct ImplT : Impl {
     if (pt_full) cudaFree(pt_full);
     if (h_scal) cudaFreeHost(h_scal);
     if (h_st) cudaFreeHost(h_st);
+    for (auto &e : st_event) if (e) cudaEventDestroy(e);
     if (comm_ready) ncclCommDestroy(comm);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -282,6 +284,7 @@ struct ImplT : Impl {
     stats.linearize_ms += ev_sum(ev_lin);
     stats.pcg_loop_ms += ev_sum(ev_pcg);
     stats.solve_ms += ev_sum(ev_solve);
+    stats.pcg_cam_ms += ev_sum(ev_cam);  // summed device time of the camera-space PCG kernel
     ev_used = 0;
   }
 
@@ -326,8 +329,9 @@ struct ImplT : Impl {
     add(&d.cm_part, (size_t)g.nChunks * 54);
     add(&d.HppD, 81 * nC); add(&d.HppInv, 81 * nC); add(&d.HllInv, 9 * nPl); add(&d.w, 3 * nPl);
     add(&d.dxc, 9 * nC); add(&d.dxl, 3 * nPl); add(&d.dxc_bk, 9 * nC); add(&d.dxl_bk, 3 * nPl);
-    add(&d.sA, 2 * (size_t)NREP * 9 * nC);  // sA[NREP][9nC] followed by sB[NREP][9nC]
+    add(&d.sA, 3 * (size_t)NREP * 9 * nC);  // sA[NREP][9nC] followed by sB[2][NREP][9nC]
     add(&d.r, 9 * nC); add(&d.p, 9 * nC); add(&d.q, 9 * nC); add(&d.z, 9 * nC); add(&d.xbk, 9 * nC);
+    add(&d.xpad, (size_t)CamPad<T>::N * nC);
     add(&d.st, 1); add(&d.scal, S_COUNT); add(&d.partials, nPart);
     size_t total = 0;
     for (auto &it : items) total += (it.bytes + 255) / 256 * 256 + 256;
@@ -370,7 +374,9 @@ struct ImplT : Impl {
     BA_CUDA(up(cm_pt, g.cm_pt.data(), sizeof(int) * nEl));
     BA_CUDA(up(cm_obs, h_cm_obs.data(), sizeof(T) * 2 * nEl));
     BA_CUDA(cudaHostAlloc(&h_scal, sizeof(double) * S_COUNT, cudaHostAllocDefault));
-    BA_CUDA(cudaHostAlloc(&h_st, sizeof(PcgState), cudaHostAllocDefault));
+    BA_CUDA(cudaHostAlloc(&h_st, 2 * sizeof(PcgState), cudaHostAllocDefault));
+    BA_CUDA(cudaEventCreateWithFlags(&st_event[0], cudaEventDisableTiming));
+    BA_CUDA(cudaEventCreateWithFlags(&st_event[1], cudaEventDisableTiming));
     if (opt.world_size > 1) BA_CUDA(cudaMalloc(&pt_full, sizeof(T) * 3 * g.nP));
     BA_CUDA(cudaStreamSynchronize(stream));
     // free the big host staging vectors that are no longer needed
@@ -480,10 +486,10 @@ struct ImplT : Impl {
   }
 
   // ---- HP2 --------------------------------------------------------------------
-  int schur_edge(int mode, const T *xin, T *sout, int check_active, bool timed) {
+  int schur_edge(int mode, const T *xin, T *sout, int check_active, bool timed, T *zero_set = nullptr) {
     size_t ev = 0;
     if (timing && timed) ev = ev_begin();
-    BA_CUDA(launch_schur_edge<T>(d, mode, xin, sout, check_active, stream));
+    BA_CUDA(launch_schur_edge<T>(d, mode, xin, sout, zero_set, check_active, stream));
     if (timing && timed) { ev_end(ev); ev_schur.push_back(ev); }
     stats.launches += d.nT > 0 ? 1 : 0;
     if (timed) stats.schur_apply_calls += 1;
@@ -498,55 +504,86 @@ struct ImplT : Impl {
     if (timing) ev_s = ev_begin();
     const bool multi = opt.world_size > 1;
     const int nrep = multi ? 1 : NREP;  // multi-GPU: replicas are folded before the allreduce
-    BA_CUDA(cudaMemsetAsync(d.sA, 0, sizeof(T) * 2 * NREP * 9 * g.nC, stream));
+    BA_CUDA(cudaMemsetAsync(d.sA, 0, sizeof(T) * 3 * NREP * 9 * g.nC, stream));
+    const size_t set_sz = (size_t)NREP * 9 * g.nC;  // sB set k lives at d.sB + k * set_sz
     BA_CUDA(launch_prep<T>(d, stream));
     stats.launches += launches_of_prep();
     BA_TRY(schur_edge(SM_MAKEV, nullptr, d.sA, 0, false));  // sA = Hpl w
-    BA_TRY(schur_edge(SM_FULL, d.dxc, d.sB, 0, true));      // sB = Hpl Hll^-1 Hlp x0
+    BA_CUDA(launch_pad_cam<T>(d, d.dxc, stream));
+    stats.launches += 1;
+    BA_TRY(schur_edge(SM_FULL, d.xpad, d.sB, 0, true));     // sB = Hpl Hll^-1 Hlp x0
     if (multi) {
       BA_CUDA(launch_fold_replicas<T>(d, d.sA, 2, stream));
       stats.launches += 1;
       BA_TRY(allreduce_T(d.sA, 9 * (size_t)g.nC));
       BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
     }
-    BA_CUDA(launch_pcg_init<T>(d, o->max_iter, o->tol, o->refuse_ratio, nrep, stream));
+    BA_CUDA(launch_pcg_init<T>(d, d.sB, o->max_iter, o->tol, o->refuse_ratio, nrep, stream));
     stats.launches += 1;
     if (timing) ev_p = ev_begin();
-    int launched = 0, n_seen = 0;
-    while (launched < o->max_iter) {
-      const int n = std::min(pcg_chunk, o->max_iter - launched);
-      const size_t ev_mark = ev_schur.size();
-      for (int i = 0; i < n; ++i) {
-        BA_TRY(schur_edge(SM_FULL, d.p, d.sB, 1, true));
-        if (multi) {
-          BA_CUDA(launch_fold_replicas<T>(d, d.sB, 1, stream));
-          stats.launches += 1;
-          BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
+    // The loop is enqueued in chunks; the device-side `active` flag turns the remaining launches of a
+    // chunk into no-ops once the reference's do-while would have exited.  The state of chunk k is polled
+    // only after chunk k+1 has been enqueued, so the GPU never waits for the host.
+    int launched = 0, n_seen = 0, chunk_id = 0;
+    struct Pending { size_t ev_mark, evc_mark; int slot; bool valid; } pend{0, 0, 0, false};
+    bool finished = false;
+    auto poll = [&](const Pending &pd) -> int {
+      BA_CUDA(cudaEventSynchronize(st_event[pd.slot]));
+      const PcgState &hs = h_st[pd.slot];
+      if (!hs.active) {
+        // launches issued after the loop ended returned immediately: keep only the event pairs of the
+        // iterations that really ran (this also drops the pairs of an over-enqueued later chunk)
+        if (timing) {
+          ev_schur.resize(pd.ev_mark + (size_t)(hs.n - n_seen));
+          ev_cam.resize(pd.evc_mark + (size_t)(hs.n - n_seen));
         }
-        BA_CUDA(launch_pcg_step<T>(d, nrep, stream));
+        finished = true;
+      }
+      n_seen = hs.n;
+      return BA_OK;
+    };
+    while (launched < o->max_iter && !finished) {
+      const int n = std::min(pcg_chunk, o->max_iter - launched);
+      const size_t ev_mark = ev_schur.size(), evc_mark = ev_cam.size();
+      for (int i = 0; i < n; ++i) {
+        // iteration it accumulates into set (it+1)&1 and clears set it&1 (read by the previous camera kernel)
+        const int it = launched + i;
+        T *cur = d.sB + (size_t)((it + 1) & 1) * set_sz, *other = d.sB + (size_t)(it & 1) * set_sz;
+        BA_TRY(schur_edge(SM_FULL, d.xpad, cur, 1, true, other));  // xpad holds p (written by the camera kernel)
+        if (multi) {
+          BA_CUDA(launch_fold_replicas<T>(d, cur, 1, stream));
+          stats.launches += 1;
+          BA_TRY(allreduce_T(cur, 9 * (size_t)g.nC));
+        }
+        size_t evc = 0;
+        if (timing) evc = ev_begin();
+        BA_CUDA(launch_pcg_step<T>(d, cur, nrep, stream));
+        if (timing) { ev_end(evc); ev_cam.push_back(evc); }
         stats.launches += 1;
       }
       launched += n;
-      BA_CUDA(cudaMemcpyAsync(h_st, d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
-      BA_CUDA(cudaStreamSynchronize(stream));
-      // edge launches issued after the loop ended returned immediately: keep only the
-      // event pairs of iterations that really ran
-      if (timing) ev_schur.resize(ev_mark + (size_t)(h_st->n - n_seen));
-      n_seen = h_st->n;
-      if (!h_st->active) break;
+      const int slot = chunk_id++ & 1;
+      BA_CUDA(cudaMemcpyAsync(&h_st[slot], d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+      BA_CUDA(cudaEventRecord(st_event[slot], stream));
+      if (pend.valid) BA_TRY(poll(pend));
+      pend = Pending{ev_mark, evc_mark, slot, true};
     }
-    if (o->max_iter <= 0) {
-      BA_CUDA(cudaMemcpyAsync(h_st, d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+    if (pend.valid && !finished) BA_TRY(poll(pend));
+    {
+      // final state (also covers max_iter <= 0 and the over-enqueued chunk)
+      BA_CUDA(cudaMemcpyAsync(&h_st[0], d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
       BA_CUDA(cudaStreamSynchronize(stream));
     }
     if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); }
     // inactive edge launches return immediately; only executed iterations are counted
-    stats.schur_apply_calls -= (launched - h_st->n);
-    BA_TRY(schur_edge(SM_BACKSUB, d.dxc, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
+    stats.schur_apply_calls -= (launched - h_st[0].n);
+    BA_CUDA(launch_pad_cam<T>(d, d.dxc, stream));
+    stats.launches += 1;
+    BA_TRY(schur_edge(SM_BACKSUB, d.xpad, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
     if (timing) { ev_end(ev_s); ev_solve.push_back(ev_s); }
-    stats.pcg_iters += h_st->n;
-    if (iters) *iters = h_st->n;
-    if (done) *done = h_st->done;
+    stats.pcg_iters += h_st[0].n;
+    if (iters) *iters = h_st[0].n;
+    if (done) *done = h_st[0].done;
     have_step = true;
     return BA_OK;
   }
@@ -696,7 +733,8 @@ struct ImplT : Impl {
     stats.launches += launches_of_prep();
     BA_CUDA(cudaMemsetAsync(d.sB, 0, sizeof(T) * NREP * 9 * g.nC, stream));
     BA_CUDA(cudaMemcpyAsync(d.z, p_v, sizeof(T) * 9 * g.nC, cudaMemcpyHostToDevice, stream));
-    BA_TRY(schur_edge(SM_FULL, d.z, d.sB, 0, true));
+    BA_CUDA(launch_pad_cam<T>(d, d.z, stream));
+    BA_TRY(schur_edge(SM_FULL, d.xpad, d.sB, 0, true));
     BA_CUDA(launch_fold_replicas<T>(d, d.sB, 1, stream));
     BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
     BA_CUDA(launch_cam_matvec_sub<T>(d, d.z, d.sB, d.q, stream));

@@ -24,6 +24,10 @@ constexpr int NTRI = 45;       // upper triangle of a 9x9 block
 constexpr int NREP = 16;        // replicas of the camera-space scatter target (spreads REDs over L2 slices)
 constexpr int AUX_GRID = 296;   // 2 CTAs per SM for the small grid-stride kernels
 
+template <typename T> struct CamPad;
+template <> struct CamPad<double> { static constexpr int N = 10; using vec = double2; };  // 80 B rows
+template <> struct CamPad<float> { static constexpr int N = 12; using vec = float4; };    // 48 B rows
+
 struct PcgState {
   double rho, rho_prev, rho_min, alpha, pq;
   double tol, refuse;
@@ -65,8 +69,10 @@ struct Dev {
   T *HllInv, *w;                // [nPl][9], [nPl][3]
   T *dxc, *dxl;                 // step: [9nC], [3nPl]
   T *dxc_bk, *dxl_bk;           // LM backup of the step (warm start after a reject)
-  T *sA, *sB;                   // [NREP][9nC] each, contiguous: edge-kernel scatter targets (replicated)
+  T *sA, *sB;                   // sA[NREP][9nC], sB[2][NREP][9nC]: edge-kernel scatter targets (replicated;
+                                // sB has two sets used alternately so the idle one can be cleared by the edge pass)
   T *r, *p, *q, *z, *xbk;       // PCG vectors [9nC]
+  T *xpad;                      // [nC][CamPad::N] padded copy of the vector the edge kernel gathers
   PcgState *st;
   double *scal;                 // [S_COUNT]
   double *partials;             // per-CTA partial sums
@@ -76,12 +82,13 @@ struct Dev {
 // ---- launchers (ba_kernels.cu); all enqueue on `st` and return cudaGetLastError ----
 template <typename T> cudaError_t launch_linearize(const Dev<T> &d, cudaStream_t st);
 enum SchurMode { SM_FULL = 0, SM_MAKEV = 1, SM_BACKSUB = 2 };
-template <typename T> cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, int check_active,
-                                                    cudaStream_t st);
+template <typename T> cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set,
+                                                    int check_active, cudaStream_t st);
 template <typename T> cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st);
-template <typename T> cudaError_t launch_pcg_init(const Dev<T> &d, int max_iter, double tol, double refuse, int nrep, cudaStream_t st);
-template <typename T> cudaError_t launch_pcg_step(const Dev<T> &d, int nrep, cudaStream_t st);
+template <typename T> cudaError_t launch_pcg_init(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep, cudaStream_t st);
+template <typename T> cudaError_t launch_pcg_step(const Dev<T> &d, T *sB, int nrep, cudaStream_t st);
 template <typename T> cudaError_t launch_fold_replicas(const Dev<T> &d, T *s, int nvec, cudaStream_t st);
+template <typename T> cudaError_t launch_pad_cam(const Dev<T> &d, const T *src, cudaStream_t st);
 int pcg_cluster_size();
 template <typename T> cudaError_t launch_trial(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_norms(const Dev<T> &d, cudaStream_t st);

@@ -21,6 +21,7 @@
 //       (src/edge/update.cu:14-41, src/algo/lm_algo.cu:61-126).
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "ba_geometry.cuh"
 #include "ba_internal.h"
@@ -28,6 +29,10 @@
 namespace cg = cooperative_groups;
 
 namespace ba {
+
+#ifndef BA_DEFAULT_VAR
+#define BA_DEFAULT_VAR 5
+#endif
 
 // --------------------------------------------------------------------------------
 // small helpers
@@ -398,20 +403,106 @@ __device__ __forceinline__ void warp_scatter9(T *sv, int *sc, const T *o, int c,
   __syncwarp();
 }
 
-template <typename T, bool IMPLICIT, int MODE>
-__global__ void __launch_bounds__(TE) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, int check_active) {
+// Camera-side gather, the mirror image of warp_scatter9: lanes read consecutive components of one
+// camera (a few 32 B sectors per instruction instead of 32 different lines), stage them in shared
+// memory and each lane then picks up the 9 values of its own observation.
+template <typename T>
+__device__ __forceinline__ const T *warp_gather9(T *sv, int *sc, const T *__restrict__ xin, int c) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T *mine = sv + (size_t)w * 32 * 9;
+  int *cams = sc + w * 32;
+  cams[lane] = c;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int v = j * 32 + lane, el = v / 9, k = v - 9 * el;
+    const int cc = cams[el];
+    mine[v] = cc >= 0 ? __ldg(xin + 9 * (size_t)cc + k) : T(0);
+  }
+  __syncwarp();
+  return mine + lane * 9;  // this lane's 9 values (stride 9 scalars: bank-conflict free)
+}
+
+// Camera-space vectors consumed by the edge kernel are kept in a padded copy (stride CamPad::N scalars,
+// 16-byte aligned rows) so that one lane fetches its camera's 9 values with 16-byte loads.
+template <typename T, bool VEC>
+__device__ __forceinline__ void gather_cam(const T *__restrict__ xpad, int c, T *x) {
+  const T *src = xpad + (size_t)CamPad<T>::N * c;
+  if (VEC) {
+    using V = typename CamPad<T>::vec;
+    constexpr int NV = CamPad<T>::N * sizeof(T) / 16;
+    V *xv = reinterpret_cast<V *>(x);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) xv[k] = __ldg(reinterpret_cast<const V *>(src) + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) x[k] = __ldg(src + k);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_pad_cam(const T *__restrict__ src, T *dst, int nC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * nC) return;
+  const int c = i / 9, k = i - 9 * c;
+  dst[(size_t)CamPad<T>::N * c + k] = src[i];
+}
+
+template <int N>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gsrc), "n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// VAR bits (design-space switches kept for measurement, see profiles/):
+//   1 = camera values gathered with 16-byte vector loads from the padded copy (5 instead of 9 tag lookups per lane)
+//   2 = W/J loads use the evict-first (streaming) policy
+//   4 = the tile's Hll^-1 blocks / w vectors are prefetched into shared memory with cp.async at kernel start
+template <typename T, int MODE, int VAR>
+__host__ __device__ constexpr size_t schur_smem_bytes() {
+  return sizeof(T) * (6 * TE + 9 * TE + ((VAR & 4) ? 12 * TE : 0)) + sizeof(int) * TE;
+}
+
+template <typename T, bool IMPLICIT, int MODE, int VAR>
+__global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active, int abl) {
   constexpr int K = IMPLICIT ? 24 : 27;
+  constexpr bool VEC = (VAR & 1) != 0, LDCS = (VAR & 2) != 0, PREF = (VAR & 4) != 0;
   if (check_active && !d.st->active) return;
-  __shared__ T sh_t[3][TE];
-  __shared__ T sh_u[3][TE];
-  __shared__ T sv[MODE != SM_BACKSUB ? TE * 9 : 1];
-  __shared__ int sc[MODE != SM_BACKSUB ? TE : 1];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sh_t = reinterpret_cast<T *>(smem_raw);  // [3][TE]
+  T *sh_u = sh_t + 3 * TE;                    // [3][TE]
+  T *sv = sh_u + 3 * TE;                      // [TE*9] gather / scatter staging
+  T *hv = sv + 9 * TE;                        // [TE*9] prefetched Hll^-1 (PREF only)
+  T *hw = hv + (PREF ? 9 * TE : 0);           // [TE*3] prefetched w      (PREF only)
+  int *sc = reinterpret_cast<int *>(hw + (PREF ? 3 * TE : 0));
   const int4 td = d.tile[blockIdx.x];
   const int slot0 = td.x, ne = td.y, pt0 = td.z, np = td.w;
   const int tid = threadIdx.x;
   T *dst = MODE != SM_BACKSUB ? sout + (size_t)(blockIdx.x % NREP) * (9 * (size_t)d.nC) : nullptr;
+  if (MODE == SM_FULL && zero_set) {  // clear the replica set the NEXT edge pass will accumulate into
+    const size_t tot = (size_t)NREP * 9 * d.nC;
+    for (size_t i = (size_t)blockIdx.x * TE + tid; i < tot; i += (size_t)gridDim.x * TE) zero_set[i] = T(0);
+  }
   if (ne <= TE) {
     const bool valid = tid < ne;
+    if (PREF) {
+      if (MODE != SM_MAKEV) {
+        const T *src = d.HllInv + 9 * (size_t)pt0;
+        for (int i = tid; i < 9 * np; i += TE) cp_async<sizeof(T)>(hv + i, src + i);
+      }
+      if (MODE != SM_FULL) {
+        const T *src = d.w + 3 * (size_t)pt0;
+        for (int i = tid; i < 3 * np; i += TE) cp_async<sizeof(T)>(hw + i, src + i);
+      }
+      cp_async_commit();
+    }
+    int s0 = 0, s1 = 0;
+    if (MODE != SM_MAKEV && tid < np) {
+      s0 = d.pt_slot[pt0 + tid] - slot0;
+      s1 = (tid + 1 < np) ? d.pt_slot[pt0 + tid + 1] - slot0 : ne;
+    }
     T wj[K];
     int c = 0, lp = 0;
     if (valid) {
@@ -420,51 +511,58 @@ __global__ void __launch_bounds__(TE) k_schur_edge(Dev<T> d, const T *__restrict
       lp = d.e_lp[slot];
       const T *src = d.WJ + wj_base<T>(slot, K);
 #pragma unroll
-      for (int k = 0; k < K; ++k) wj[k] = __ldg(src + (size_t)k * TE);
-      if (MODE != SM_MAKEV) {
-        T x[9], t[3];
-#pragma unroll
-        for (int y = 0; y < 9; ++y) x[y] = __ldg(xin + 9 * (size_t)c + y);
-        edge_t<T, IMPLICIT>(wj, x, t);
-        sh_t[0][tid] = t[0]; sh_t[1][tid] = t[1]; sh_t[2][tid] = t[2];
-      }
+      for (int k = 0; k < K; ++k) wj[k] = LDCS ? __ldcs(src + (size_t)k * TE) : __ldg(src + (size_t)k * TE);
     }
-    if (MODE != SM_MAKEV) __syncthreads();
+    if (MODE != SM_MAKEV) {
+      T t[3];
+      if (valid) {
+        __align__(16) T x[CamPad<T>::N];
+        if (abl & 2) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) x[k] = T(1);
+        } else {
+          gather_cam<T, VEC>(xin, c, x);
+        }
+        edge_t<T, IMPLICIT>(wj, x, t);
+      }
+      if (valid) { sh_t[tid] = t[0]; sh_t[TE + tid] = t[1]; sh_t[2 * TE + tid] = t[2]; }
+    }
+    if (PREF) cp_async_wait_all();
+    if (MODE != SM_MAKEV || PREF) __syncthreads();
     if (tid < np) {
       const int p = pt0 + tid;
       T u[3];
       if (MODE != SM_MAKEV) {
-        const int s0 = d.pt_slot[p] - slot0;
-        const int s1 = (tid + 1 < np) ? d.pt_slot[p + 1] - slot0 : ne;
         T t0 = T(0), t1 = T(0), t2 = T(0);
-        for (int s = s0; s < s1; ++s) { t0 += sh_t[0][s]; t1 += sh_t[1][s]; t2 += sh_t[2][s]; }
+        if (abl & 4) { s1 = s0 + 1; }
+        for (int s = s0; s < s1; ++s) { t0 += sh_t[s]; t1 += sh_t[TE + s]; t2 += sh_t[2 * TE + s]; }
         T hi[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInv + 9 * (size_t)p + k);
+        for (int k = 0; k < 9; ++k) hi[k] = PREF ? hv[9 * tid + k] : __ldg(d.HllInv + 9 * (size_t)p + k);
 #pragma unroll
         for (int y = 0; y < 3; ++y) u[y] = hi[3 * y] * t0 + hi[3 * y + 1] * t1 + hi[3 * y + 2] * t2;
         if (MODE == SM_BACKSUB) {
 #pragma unroll
-          for (int y = 0; y < 3; ++y) d.dxl[3 * (size_t)p + y] = d.w[3 * (size_t)p + y] - u[y];
+          for (int y = 0; y < 3; ++y) d.dxl[3 * (size_t)p + y] = (PREF ? hw[3 * tid + y] : d.w[3 * (size_t)p + y]) - u[y];
         }
       } else {
 #pragma unroll
-        for (int y = 0; y < 3; ++y) u[y] = d.w[3 * (size_t)p + y];
+        for (int y = 0; y < 3; ++y) u[y] = PREF ? hw[3 * tid + y] : d.w[3 * (size_t)p + y];
       }
-      if (MODE != SM_BACKSUB) { sh_u[0][tid] = u[0]; sh_u[1][tid] = u[1]; sh_u[2][tid] = u[2]; }
+      if (MODE != SM_BACKSUB) { sh_u[tid] = u[0]; sh_u[TE + tid] = u[1]; sh_u[2 * TE + tid] = u[2]; }
     }
     if (MODE != SM_BACKSUB) {
       __syncthreads();
       T o[9];
       if (valid) {
-        const T u[3] = {sh_u[0][lp], sh_u[1][lp], sh_u[2][lp]};
+        const T u[3] = {sh_u[lp], sh_u[TE + lp], sh_u[2 * TE + lp]};
         edge_scatter<T, IMPLICIT>(wj, u, o);
       }
-      warp_scatter9<T>(sv, sc, o, valid ? c : -1, dst);
+      if (!(abl & 1)) warp_scatter9<T>(sv, sc, o, valid ? c : -1, dst);
+      else if (valid && o[0] == T(123.456)) dst[0] = o[1];
     }
   } else {
-    // a single point with more than TE observations: two passes over its slabs
-    T *smT = &sh_t[0][0];
+    // a single point with more than TE observations: two passes over its slabs (rare; simple path)
     T u[3];
     if (MODE != SM_MAKEV) {
       T t[3] = {T(0), T(0), T(0)};
@@ -472,15 +570,15 @@ __global__ void __launch_bounds__(TE) k_schur_edge(Dev<T> d, const T *__restrict
         const int slot = slot0 + i;
         const int c = d.e_cam[slot];
         const T *src = d.WJ + wj_base<T>(slot, K);
-        T wj[K], x[9], te[3];
+        T wj[K], te[3];
+        __align__(16) T x[CamPad<T>::N];
 #pragma unroll
         for (int k = 0; k < K; ++k) wj[k] = __ldg(src + (size_t)k * TE);
-#pragma unroll
-        for (int y = 0; y < 9; ++y) x[y] = __ldg(xin + 9 * (size_t)c + y);
+        gather_cam<T, false>(xin, c, x);
         edge_t<T, IMPLICIT>(wj, x, te);
         t[0] += te[0]; t[1] += te[1]; t[2] += te[2];
       }
-      const T t0 = block_sum<T>(t[0], smT), t1 = block_sum<T>(t[1], smT), t2 = block_sum<T>(t[2], smT);
+      const T t0 = block_sum<T>(t[0], sh_t), t1 = block_sum<T>(t[1], sh_t), t2 = block_sum<T>(t[2], sh_t);
       T hi[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInv + 9 * (size_t)pt0 + k);
@@ -543,7 +641,7 @@ __device__ __forceinline__ double cluster_sum(double v, double *red_warp, double
 // INIT = 1: r = (g_c - sA) - (HppD x0 - sB); z = M^-1 r; rho; p = z      (:182-258,268-313 at n = 0)
 // INIT = 0: bottom half of iteration n + top half of iteration n+1          (:359-406, :268-313)
 template <typename T, int INIT>
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter, double tol, double refuse, int nrep) {
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, T *sB, int max_iter, double tol, double refuse, int nrep) {
   cg::cluster_group cl = cg::this_cluster();
   __shared__ double red_warp[32];
   __shared__ double slots[2];
@@ -564,9 +662,9 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter,
   T *x = d.dxc;
   // fold the replicas of the scatter targets into replica 0 (own rows only)
   for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
-    T a = d.sB[i];
-    for (int rep = 1; rep < nrep; ++rep) a += d.sB[rep * rs + i];
-    d.sB[i] = a;
+    T a = sB[i];
+    for (int rep = 1; rep < nrep; ++rep) a += sB[rep * rs + i];
+    sB[i] = a;
     if (INIT) {
       T b = d.sA[i];
       for (int rep = 1; rep < nrep; ++rep) b += d.sA[rep * rs + i];
@@ -581,7 +679,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter,
 #pragma unroll
       for (int j = 0; j < 9; ++j) a += d.HppD[81 * (size_t)c + 9 * k + j] * x[9 * c + j];
       const T v = d.gc[i] - d.sA[i];            // v = g_c - Hpl w          (:478-493)
-      d.r[i] = v - (a - d.sB[i]);               // r = v - (Hpp x0 - Hpl Hll^-1 Hlp x0)
+      d.r[i] = v - (a - sB[i]);               // r = v - (Hpp x0 - Hpl Hll^-1 Hlp x0)
     }
   } else {
     double acc = 0.;
@@ -590,7 +688,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter,
       T a = T(0);
 #pragma unroll
       for (int j = 0; j < 9; ++j) a += d.HppD[81 * (size_t)c + 9 * k + j] * d.p[9 * c + j];
-      const T qi = a - d.sB[i];                 // q = Hpp p - Hpl Hll^-1 Hlp p   (:359-366)
+      const T qi = a - sB[i];                 // q = Hpp p - Hpl Hll^-1 Hlp p   (:359-366)
       d.q[i] = qi;
       acc += (double)(d.p[i] * qi);
     }
@@ -633,17 +731,22 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter,
       st.rho_min = fmin(st.rho_min, rho_new);   // :296
       if (!INIT) {
         const T beta = (T)(rho_new / st.rho);   // :299
-        for (int i = i0 + tid; i < i1; i += PCG_THREADS) d.p[i] = d.z[i] + beta * d.p[i];
+        for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
+          const T pv = d.z[i] + beta * d.p[i];
+          d.p[i] = pv;
+          d.xpad[(size_t)CamPad<T>::N * (i / 9) + i % 9] = pv;
+        }
       } else {
-        for (int i = i0 + tid; i < i1; i += PCG_THREADS) d.p[i] = d.z[i];  // :310
+        for (int i = i0 + tid; i < i1; i += PCG_THREADS) {  // :310
+          d.p[i] = d.z[i];
+          d.xpad[(size_t)CamPad<T>::N * (i / 9) + i % 9] = d.z[i];
+        }
       }
       st.rho_prev = st.rho;
       st.rho = rho_new;
     }
   }
   st.active = cont ? 1 : 0;
-  for (int rep = 0; rep < nrep; ++rep)
-    for (int i = i0 + tid; i < i1; i += PCG_THREADS) d.sB[rep * rs + i] = T(0);  // ready for the next edge pass
   cl.sync();  // nobody leaves while peers may still read its slots; st is written after every read
   if (rank == 0 && tid == 0) *d.st = st;
 }
@@ -652,7 +755,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, int max_iter,
 // vectors and keeps their Hpp / Hpp^-1 rows, p, r, x in registers for the whole kernel, so the kernel
 // is one L2 round trip + two cluster reductions instead of a chain of dependent global round trips.
 template <typename T, int INIT, int RPT, bool PRE_INV>
-__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int max_iter, double tol, double refuse, int nrep) {
+__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const T *__restrict__ sB, int max_iter, double tol, double refuse, int nrep) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red_warp[32];
@@ -665,7 +768,17 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int ma
     st = *d.st;
     if (!st.active) return;
   }
+  const int cut = nrep >> 8;
+  nrep &= 255;
   const int ncta = cl.num_blocks(), rank = cl.block_rank();
+#define BA_CUT(k, dep)                                                        \
+  if (!INIT && cut == k) {                                                    \
+    if (rank == 0 && threadIdx.x == 0) {                                      \
+      st.n += 1; st.active = st.n < st.max_iter; st.rho = 1. + 1e-300 * (double)(dep); *d.st = st; \
+    }                                                                         \
+    return;                                                                   \
+  }
+  BA_CUT(1, 0)
   const int per = (d.nC + ncta - 1) / ncta;
   const int c0 = min(d.nC, rank * per), c1 = min(d.nC, c0 + per);
   const int i0 = 9 * c0, nrows = 9 * (c1 - c0);
@@ -673,6 +786,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int ma
   const size_t rs = 9 * (size_t)d.nC;
   T *p_s = reinterpret_cast<T *>(smraw);
   T *r_s = p_s + RPT * PCG_THREADS;
+  T *hi_s = r_s + RPT * PCG_THREADS;  // [RPT*PCG_THREADS][9], only when !PRE_INV
   T hd[RPT][9], hi[PRE_INV ? RPT : 1][9], pj[RPT], rj[RPT], xj[RPT], xb[RPT], sj[RPT], qj[RPT], zj[RPT];
   // ---- one wave of independent loads
 #pragma unroll
@@ -686,14 +800,25 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int ma
       if (PRE_INV) {
 #pragma unroll
         for (int m = 0; m < 9; ++m) hi[j][m] = __ldg(d.HppInv + 81 * (size_t)c + 9 * k + m);
+      } else {
+#pragma unroll
+        for (int m = 0; m < 9; ++m) cp_async<sizeof(T)>(hi_s + 9 * (size_t)l + m, d.HppInv + 81 * (size_t)c + 9 * k + m);
       }
       xj[j] = d.dxc[i];
+      // all replica loads are issued before the first add (a rolled loop would serialise 16 L2 round trips)
+      T sbv[NREP];
+#pragma unroll
+      for (int rep = 0; rep < NREP; ++rep) sbv[rep] = rep < nrep ? sB[rep * rs + i] : T(0);
       T sb = T(0);
-      for (int rep = 0; rep < nrep; ++rep) sb += d.sB[rep * rs + i];
+#pragma unroll
+      for (int rep = 0; rep < NREP; ++rep) sb += sbv[rep];
       sj[j] = sb;
       if (INIT) {
+#pragma unroll
+        for (int rep = 0; rep < NREP; ++rep) sbv[rep] = rep < nrep ? d.sA[rep * rs + i] : T(0);
         T sa = T(0);
-        for (int rep = 0; rep < nrep; ++rep) sa += d.sA[rep * rs + i];
+#pragma unroll
+        for (int rep = 0; rep < NREP; ++rep) sa += sbv[rep];
         pj[j] = xj[j];               // operand of Hpp x0
         rj[j] = d.gc[i] - sa;        // v = g_c - Hpl w                      (:478-493)
       } else {
@@ -703,6 +828,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int ma
       p_s[l] = pj[j];
     }
   }
+  if (!PRE_INV) cp_async_commit();
   __syncthreads();
   double acc = 0.;
 #pragma unroll
@@ -718,8 +844,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int ma
       else acc += (double)(pj[j] * qj[j]);
     }
   }
+  BA_CUT(2, acc)
   if (!INIT) {
     const double pq = cluster_sum(acc, red_warp, &slots[0], cl);
+    BA_CUT(3, pq)
     const T alpha = (T)(st.rho / pq);          // :385
     st.alpha = (double)alpha; st.pq = pq;
 #pragma unroll
@@ -734,24 +862,27 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int ma
     const int l = tid + j * PCG_THREADS;
     if (l < nrows) r_s[l] = rj[j];
   }
+  if (!PRE_INV) cp_async_wait_all();  // each thread reads back only the rows it copied itself
   __syncthreads();
   acc = 0.;
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     const int l = tid + j * PCG_THREADS;
     if (l < nrows) {
-      const int i = i0 + l, c = i / 9, k = i - 9 * c, lc = l - k;
+      const int lc = l - (i0 + l) % 9;
       T a = T(0);
 #pragma unroll
       for (int m = 0; m < 9; ++m) {
-        const T h = PRE_INV ? hi[j][m] : __ldg(d.HppInv + 81 * (size_t)c + 9 * k + m);
+        const T h = PRE_INV ? hi[j][m] : hi_s[9 * (size_t)l + m];
         a += h * r_s[lc + m];
       }
       zj[j] = a;                               // z = M^-1 r                    (:273-275)
       acc += (double)(rj[j] * a);
     }
   }
+  BA_CUT(4, acc)
   const double rho_new = (double)(T)cluster_sum(acc, red_warp, &slots[1], cl);
+  BA_CUT(5, rho_new)
   bool cont = true, refused = false;
   if (!INIT) {
     st.n += 1;                                 // :405
@@ -784,11 +915,15 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, int ma
         d.dxc[i] = refused ? xb[j] : xj[j];
         d.xbk[i] = xb[j];
       }
-      if (cont) d.p[i] = INIT ? zj[j] : zj[j] + beta * pj[j];  // :310 / :299-306
-      for (int rep = 0; rep < nrep; ++rep) d.sB[rep * rs + i] = T(0);
+      if (cont) {
+        const T pv = INIT ? zj[j] : zj[j] + beta * pj[j];  // :310 / :299-306
+        d.p[i] = pv;
+        d.xpad[(size_t)CamPad<T>::N * (i / 9) + i % 9] = pv;
+      }
     }
   }
-  cl.sync();
+  // lifetime barrier only (peers may still read this CTA's slots): relaxed, so it does not wait for the stores above
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
   if (rank == 0 && tid == 0) *d.st = st;
 }
 
@@ -965,26 +1100,62 @@ cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st) {
 }
 int launches_of_prep() { return 2; }
 
+static int schur_ablation() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("BA_ABL"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+int schur_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("BA_VAR");
+    v = e ? (atoi(e) & 7) : BA_DEFAULT_VAR;
+  }
+  return v;
+}
+
+template <typename T, bool IMPLICIT, int MODE, int VAR>
+static void launch_schur_edge_v(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  auto kern = k_schur_edge<T, IMPLICIT, MODE, VAR>;
+  constexpr size_t smem = schur_smem_bytes<T, MODE, VAR>();
+  static bool prepared = false;
+  if (!prepared) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prepared = true;
+  }
+  kern<<<d.nT, TE, smem, st>>>(d, xin, sout, zero_set, check_active, schur_ablation());
+}
+
+template <typename T, bool IMPLICIT, int MODE>
+static void launch_schur_edge_m(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  switch (schur_variant()) {
+#define BA_V(n) case n: launch_schur_edge_v<T, IMPLICIT, MODE, n>(d, xin, sout, zero_set, check_active, st); break;
+    BA_V(0) BA_V(1) BA_V(2) BA_V(3) BA_V(4) BA_V(5) BA_V(6) BA_V(7)
+#undef BA_V
+  }
+}
+
 template <typename T, bool IMPLICIT>
-static void launch_schur_edge_t(const Dev<T> &d, int mode, const T *xin, T *sout, int check_active, cudaStream_t st) {
+static void launch_schur_edge_t(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
   switch (mode) {
-    case SM_FULL: k_schur_edge<T, IMPLICIT, SM_FULL><<<d.nT, TE, 0, st>>>(d, xin, sout, check_active); break;
-    case SM_MAKEV: k_schur_edge<T, IMPLICIT, SM_MAKEV><<<d.nT, TE, 0, st>>>(d, xin, sout, check_active); break;
-    default: k_schur_edge<T, IMPLICIT, SM_BACKSUB><<<d.nT, TE, 0, st>>>(d, xin, sout, check_active); break;
+    case SM_FULL: launch_schur_edge_m<T, IMPLICIT, SM_FULL>(d, xin, sout, zero_set, check_active, st); break;
+    case SM_MAKEV: launch_schur_edge_m<T, IMPLICIT, SM_MAKEV>(d, xin, sout, zero_set, check_active, st); break;
+    default: launch_schur_edge_m<T, IMPLICIT, SM_BACKSUB>(d, xin, sout, zero_set, check_active, st); break;
   }
 }
 
 template <typename T>
-cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, int check_active, cudaStream_t st) {
+cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
   if (d.nT == 0) return cudaSuccess;
-  if (d.implicit) launch_schur_edge_t<T, true>(d, mode, xin, sout, check_active, st);
-  else launch_schur_edge_t<T, false>(d, mode, xin, sout, check_active, st);
+  if (d.implicit) launch_schur_edge_t<T, true>(d, mode, xin, sout, zero_set, check_active, st);
+  else launch_schur_edge_t<T, false>(d, mode, xin, sout, zero_set, check_active, st);
   return cudaGetLastError();
 }
 
-template <typename K, typename T>
-static cudaError_t launch_cluster(K kernel, int cl, size_t smem, const Dev<T> &d, int max_iter, double tol, double refuse,
-                                  int nrep, cudaStream_t st) {
+template <typename K, typename T, typename P>
+static cudaError_t launch_cluster(K kernel, int cl, size_t smem, const Dev<T> &d, P sB, int max_iter, double tol,
+                                  double refuse, int nrep, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cl);
   cfg.blockDim = dim3(PCG_THREADS);
@@ -997,22 +1168,22 @@ static cudaError_t launch_cluster(K kernel, int cl, size_t smem, const Dev<T> &d
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, d, max_iter, tol, refuse, nrep);
+  return cudaLaunchKernelEx(&cfg, kernel, d, sB, max_iter, tol, refuse, nrep);
 }
 
 template <typename T, int INIT, int RPT>
-static cudaError_t launch_pcg_reg(const Dev<T> &d, int cl, int max_iter, double tol, double refuse, int nrep,
+static cudaError_t launch_pcg_reg(const Dev<T> &d, T *sB, int cl, int max_iter, double tol, double refuse, int nrep,
                                   cudaStream_t st) {
   constexpr bool PRE = RPT <= 1 || sizeof(T) == 4;
   auto kern = k_pcg_cam_reg<T, INIT, RPT, PRE>;
-  const size_t smem = 2 * (size_t)RPT * PCG_THREADS * sizeof(T);
+  const size_t smem = (2 + (PRE ? 0 : 9)) * (size_t)RPT * PCG_THREADS * sizeof(T);
   static bool prepared = false;  // per instantiation
   if (!prepared) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prepared = true;
   }
-  return launch_cluster(kern, cl, smem, d, max_iter, tol, refuse, nrep, st);
+  return launch_cluster(kern, cl, smem, d, (const T *)sB, max_iter, tol, refuse, nrep, st);
 }
 
 // 16-CTA clusters are "non-portable": ask the occupancy API once whether this device can host one.
@@ -1024,7 +1195,8 @@ int pcg_cluster_size() {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(16);
   cfg.blockDim = dim3(PCG_THREADS);
-  cfg.dynamicSmemBytes = 2 * 2 * PCG_THREADS * sizeof(double);
+  cfg.dynamicSmemBytes = 11 * 2 * PCG_THREADS * sizeof(double);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 16;
@@ -1040,24 +1212,33 @@ int pcg_cluster_size() {
 }
 
 template <typename T, int INIT>
-static cudaError_t launch_pcg_cam(const Dev<T> &d, int max_iter, double tol, double refuse, int nrep, cudaStream_t st) {
-  const int cl = pcg_cluster_size();
+static cudaError_t launch_pcg_cam(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep, cudaStream_t st) {
+  static int clenv = -1, cut = 0;
+  if (clenv < 0) { const char *e = getenv("BA_CL"); clenv = e ? atoi(e) : 0; e = getenv("BA_CAMCUT"); cut = e ? atoi(e) : 0; }
+  nrep |= cut << 8;
+  const int cl = clenv ? clenv : pcg_cluster_size();
   const int rows = 9 * ((d.nC + cl - 1) / cl);
   const int rpt = (rows + PCG_THREADS - 1) / PCG_THREADS;
-  if (rpt <= 1) return launch_pcg_reg<T, INIT, 1>(d, cl, max_iter, tol, refuse, nrep, st);
-  if (rpt <= 2) return launch_pcg_reg<T, INIT, 2>(d, cl, max_iter, tol, refuse, nrep, st);
-  if (rpt <= 4) return launch_pcg_reg<T, INIT, 4>(d, cl, max_iter, tol, refuse, nrep, st);
-  if (rpt <= 8) return launch_pcg_reg<T, INIT, 8>(d, cl, max_iter, tol, refuse, nrep, st);
-  return launch_cluster(k_pcg_cam<T, INIT>, PCG_CL, 0, d, max_iter, tol, refuse, nrep, st);
+  if (rpt <= 1) return launch_pcg_reg<T, INIT, 1>(d, sB, cl, max_iter, tol, refuse, nrep, st);
+  if (rpt <= 2) return launch_pcg_reg<T, INIT, 2>(d, sB, cl, max_iter, tol, refuse, nrep, st);
+  if (rpt <= 4) return launch_pcg_reg<T, INIT, 4>(d, sB, cl, max_iter, tol, refuse, nrep, st);
+  if (rpt <= 8) return launch_pcg_reg<T, INIT, 8>(d, sB, cl, max_iter, tol, refuse, nrep, st);
+  return launch_cluster(k_pcg_cam<T, INIT>, PCG_CL, 0, d, sB, max_iter, tol, refuse, nrep, st);
 }
 
 template <typename T>
-cudaError_t launch_pcg_init(const Dev<T> &d, int max_iter, double tol, double refuse, int nrep, cudaStream_t st) {
-  return launch_pcg_cam<T, 1>(d, max_iter, tol, refuse, nrep, st);
+cudaError_t launch_pcg_init(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep, cudaStream_t st) {
+  return launch_pcg_cam<T, 1>(d, sB, max_iter, tol, refuse, nrep, st);
 }
 template <typename T>
-cudaError_t launch_pcg_step(const Dev<T> &d, int nrep, cudaStream_t st) {
-  return launch_pcg_cam<T, 0>(d, 0, 0., 0., nrep, st);
+cudaError_t launch_pcg_step(const Dev<T> &d, T *sB, int nrep, cudaStream_t st) {
+  return launch_pcg_cam<T, 0>(d, sB, 0, 0., 0., nrep, st);
+}
+
+template <typename T>
+cudaError_t launch_pad_cam(const Dev<T> &d, const T *src, cudaStream_t st) {
+  k_pad_cam<T><<<(9 * d.nC + 255) / 256, 256, 0, st>>>(src, d.xpad, d.nC);
+  return cudaGetLastError();
 }
 
 template <typename T>
@@ -1108,11 +1289,12 @@ cudaError_t launch_cam_matvec_sub(const Dev<T> &d, const T *p, const T *s, T *q,
 
 #define BA_INSTANTIATE(T)                                                                                   \
   template cudaError_t launch_linearize<T>(const Dev<T> &, cudaStream_t);                                   \
-  template cudaError_t launch_schur_edge<T>(const Dev<T> &, int, const T *, T *, int, cudaStream_t);        \
+  template cudaError_t launch_schur_edge<T>(const Dev<T> &, int, const T *, T *, T *, int, cudaStream_t);   \
   template cudaError_t launch_prep<T>(const Dev<T> &, cudaStream_t);                                        \
-  template cudaError_t launch_pcg_init<T>(const Dev<T> &, int, double, double, int, cudaStream_t);          \
-  template cudaError_t launch_pcg_step<T>(const Dev<T> &, int, cudaStream_t);                               \
+  template cudaError_t launch_pcg_init<T>(const Dev<T> &, T *, int, double, double, int, cudaStream_t);     \
+  template cudaError_t launch_pcg_step<T>(const Dev<T> &, T *, int, cudaStream_t);                          \
   template cudaError_t launch_fold_replicas<T>(const Dev<T> &, T *, int, cudaStream_t);                     \
+  template cudaError_t launch_pad_cam<T>(const Dev<T> &, const T *, cudaStream_t);                          \
   template cudaError_t launch_trial<T>(const Dev<T> &, cudaStream_t);                                       \
   template cudaError_t launch_norms<T>(const Dev<T> &, cudaStream_t);                                       \
   template cudaError_t launch_apply_step<T>(const Dev<T> &, cudaStream_t);                                  \
