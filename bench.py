@@ -113,6 +113,41 @@ def oracle_lm_iteration(P, pcg_iters, implicit, dtype):
     return dt, sum(t["pcg_iters"] for t in tr), O.num_threads(), tr
 
 
+def reference_gpu_solver(P, pcg_lo=5, pcg_hi=25):
+    """MegBA's own SchurPCGSolver::solve (src/solver/schur_pcg_solver.cu: cuBLAS matinvBatched, cuSPARSE CSR SpMV,
+    cuBLAS dot/axpy, two host syncs per iteration) compiled for sm_100a from the reference sources via oracle/shim,
+    timed on this GPU on the same problem with the same damped blocks.  Two fixed iteration counts give the time per
+    PCG iteration by difference.  Returns None when oracle/_ref was not built (the reference is not on the GPU box)."""
+    import ctypes as C
+    lib = os.path.join(ROOT, "oracle", "_ref", "libmegba_ref.so")
+    if not os.path.exists(lib):
+        return None
+    from oracle.oracle import Oracle
+    L = C.CDLL(lib)
+    O = Oracle(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, np.float64)
+    r, J = O.forward(P.cam, P.pt)
+    Hpp, Hll, W, g = O.build(r, J)
+    HppD, _ = O.process_diag(Hpp, LM_REGION)
+    HllD, _ = O.process_diag(Hll, LM_REGION)
+    del r, J
+    ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    out = {}
+    for n in (pcg_lo, pcg_hi, pcg_lo, pcg_hi):
+        dx = np.zeros(9 * P.nC + 3 * P.nP)
+        ms = C.c_double()
+        rc = L.ref_solve_timed_f64(C.c_int64(P.nC), C.c_int64(P.nP), C.c_int64(P.nE), ptr(P.cam_idx), ptr(P.pt_idx),
+                                   ptr(HppD), ptr(HllD), ptr(W), ptr(g), ptr(dx), C.c_int(n), C.c_double(0.0),
+                                   C.c_double(1e300), C.byref(ms))
+        if rc != 0:
+            return None
+        out[n] = min(out.get(n, 1e30), ms.value)
+    per_iter = (out[pcg_hi] - out[pcg_lo]) / (pcg_hi - pcg_lo)
+    return {"pcg_iters_per_sec": 1e3 / per_iter, "ms_per_pcg_iter": per_iter,
+            "solve_ms": {str(k): v for k, v in out.items()},
+            "what": "reference SchurPCGSolver::solve (schur_pcg_solver.cu, cuSPARSE/cuBLAS) built for sm_100a via "
+                    "oracle/shim, same GPU and problem; best of 2 per iteration count, per-iteration time by difference"}
+
+
 def run_reference(args, P, dtype):
     """CPU arm: the reference has no CPU execution path (every Device::CPU branch throws) and cannot be
     built here (Eigen/gflags absent), so this times the oracle port of its algorithm on all host threads."""
@@ -287,6 +322,15 @@ def run_ours(args, P, dtype):
                "sample": f"best of 2 x [1 LM iteration = 2 linearisations + {npcg} PCG iterations] of the same "
                          f"problem, oracle port (OpenMP, {threads} threads)"}
 
+    ref_gpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline and dtype == np.float64 and not args.implicit:
+        S.close()
+        torch.cuda.empty_cache()
+        try:
+            ref_gpu = reference_gpu_solver(P)
+        except Exception as exc:  # the checker library is optional
+            ref_gpu = {"error": repr(exc)}
+
     if rank == 0:
         line = {
             "metric": "lm_iters_per_sec", "value": lm_rate, "unit": "LM it/s", "n_gpus": ws, "steps": args.steps,
@@ -296,7 +340,8 @@ def run_ours(args, P, dtype):
             "pcg_iters_per_sec": pcg_rate, "pcg_iters_timed": st["pcg_iters"],
             "accepted_steps": sum(1 for t in trace[1:] if t["accepted"] == 1),
             "wall_ms_per_step": 1e3 * wall / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "reference_gpu_solver": ref_gpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks,
             "final_cost": trace[-1]["cost"], "start_cost": trace[0]["cost"],
         }
         print(json.dumps(line), flush=True)

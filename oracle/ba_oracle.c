@@ -15,15 +15,15 @@
  *   src/algo/lm_algo.cu:26-223                    LM loop and its scalars
  * of MegviiRobot/MegBA, each function citing the lines it follows.
  *
- * PARITY UNPINNED by upstream: the reference ships no tests, golden vectors or
- * fixtures for this path, cannot be built here as a whole (Eigen submodule and
- * gflags absent, no CPU execution path), and its block inverse / SpMV / dot live
- * in closed cuBLAS / cuSPARSE.  The oracle is therefore pinned by
- *   (i)  independent mathematical checks in tests/ (central finite differences on
- *        J, dense normal-equation solve vs PCG, cost monotonicity), and
- *   (ii) where available, the reference's own CUDA kernels compiled unmodified
- *        against shim headers into oracle/_ref/ (see oracle/Makefile) and run on
- *        the GPU box by the `-m gpu` tests.
+ * Pinning: upstream ships no tests, golden vectors or fixtures for this path and has no CPU execution path, so it
+ * cannot be run here as a whole.  The oracle is pinned by
+ *   (i)  the reference's own CUDA sources for rows a2, a3, a5-a8 (analytical_derivatives.cu, build_linear_system.cu,
+ *        schur_pcg_solver.cu) compiled UNMODIFIED against shim headers into oracle/_ref/ (oracle/shim/README.md) and
+ *        run on the GPU box by tests/test_gpu_reference_pin.py against this oracle and against the product;
+ *   (ii) independent mathematics in tests/test_oracle.py (central finite differences on J, dense normal-equation
+ *        solve vs PCG, independent projection, cost monotonicity).
+ * PARITY UNPINNED for a4 (damping), a10 (LM scalars) and the a11 control law: those are restatements checked only
+ * by (ii) and by end-to-end LM traces.
  */
 #include <math.h>
 #include <stdint.h>
