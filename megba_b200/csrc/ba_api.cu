@@ -4,6 +4,7 @@
 // every numeric result is produced by the kernels in ba_kernels.cu.
 #include <cuda_runtime.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -225,6 +226,7 @@ struct Impl {
   virtual int get_stats(ba_stats *out) = 0;
   virtual int reset_stats() = 0;
   virtual int algorithmic_bytes(double *a, double *b) = 0;
+  virtual int setup_p2p() = 0;
 };
 
 template <typename T>
@@ -241,6 +243,12 @@ struct ImplT : Impl {
   size_t ev_used = 0;
   std::vector<size_t> ev_schur, ev_lin, ev_pcg, ev_solve, ev_cam;
   int pcg_chunk = 8;
+  // fused peer-memory exchange of the camera kernel (world_size > 1)
+  void *xchg = nullptr;
+  void *ipc_opened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  PeerExchange px{};
+  bool p2p = false;
+  unsigned long long px_epoch = 0;
 
   ~ImplT() override {
     if (stream) cudaStreamSynchronize(stream);
@@ -249,6 +257,8 @@ struct ImplT : Impl {
     if (e_info_dev) cudaFree(e_info_dev);
     if (cm_info_dev) cudaFree(cm_info_dev);
     if (pt_full) cudaFree(pt_full);
+    for (auto *q : ipc_opened) if (q) cudaIpcCloseMemHandle(q);
+    if (xchg) cudaFree(xchg);
     if (h_scal) cudaFreeHost(h_scal);
     if (h_st) cudaFreeHost(h_st);
     for (auto &e : st_event) if (e) cudaEventDestroy(e);
@@ -304,6 +314,59 @@ struct ImplT : Impl {
   int fetch_scalars() {
     BA_CUDA(cudaMemcpyAsync(h_scal, d.scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, stream));
     BA_CUDA(cudaStreamSynchronize(stream));
+    return BA_OK;
+  }
+
+  // Maps every rank's exchange buffer into this rank's address space (CUDA IPC across processes, plain peer
+  // access between threads of one process).  Any failure leaves p2p = false and the NCCL path in use.
+  int setup_p2p() override {
+    if (opt.world_size == 1 || opt.world_size > 8 || !comm_ready) return BA_OK;
+    BA_CUDA(cudaSetDevice(opt.device));
+    const size_t n9 = 9 * (size_t)g.nC, bytes = sizeof(T) * 4 * n9, off = (bytes + 255) / 256 * 256;
+    struct Info { cudaIpcMemHandle_t h; long long pid; unsigned long long ptr; int dev, ok; char pad[128 - sizeof(cudaIpcMemHandle_t) - 24]; };
+    static_assert(sizeof(Info) == 128, "Info is one 128-byte record");
+    Info mine{};
+    int ok = 1;
+    if (cudaMalloc(&xchg, off + 256) != cudaSuccess) { cudaGetLastError(); xchg = nullptr; ok = 0; }
+    if (ok && cudaMemset(xchg, 0, off + 256) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine.h, xchg) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    mine.pid = (long long)getpid(); mine.ptr = (unsigned long long)xchg; mine.dev = opt.device; mine.ok = ok;
+    char *scratch = reinterpret_cast<char *>(d.partials);  // >= 8 * 128 bytes
+    std::vector<Info> all(opt.world_size);
+    BA_CUDA(cudaMemcpyAsync(scratch + 128 * opt.rank, &mine, 128, cudaMemcpyHostToDevice, stream));
+    BA_NCCL(ncclAllGather(scratch + 128 * opt.rank, scratch, 128, ncclChar, comm, stream));
+    BA_CUDA(cudaMemcpyAsync(all.data(), scratch, 128 * opt.world_size, cudaMemcpyDeviceToHost, stream));
+    BA_CUDA(cudaStreamSynchronize(stream));
+    px = PeerExchange{};
+    for (int r = 0; r < opt.world_size; ++r) {
+      void *ptr = nullptr;
+      if (!all[r].ok) { ok = 0; continue; }
+      if (r == opt.rank) {
+        ptr = xchg;
+      } else if (all[r].pid == mine.pid) {  // another host thread of this process: direct peer access
+        cudaError_t e = cudaDeviceEnablePeerAccess(all[r].dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+        cudaGetLastError();
+        ptr = (void *)all[r].ptr;
+      } else if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+        ipc_opened[r] = ptr;
+      } else {
+        cudaGetLastError();
+        ok = 0;
+      }
+      px.data[r] = ptr;
+      px.flag[r] = ptr ? reinterpret_cast<unsigned long long *>((char *)ptr + off) : nullptr;
+    }
+    // every rank must take the same path: agree on min(ok)
+    double okd = ok;
+    BA_CUDA(cudaMemcpyAsync(d.scal + S_XCHG_ERR, &okd, sizeof(double), cudaMemcpyHostToDevice, stream));
+    BA_NCCL(ncclAllReduce(d.scal + S_XCHG_ERR, d.scal + S_XCHG_ERR, 1, ncclDouble, ncclMin, comm, stream));
+    BA_CUDA(cudaMemcpyAsync(&okd, d.scal + S_XCHG_ERR, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    BA_CUDA(cudaMemsetAsync(d.scal + S_XCHG_ERR, 0, sizeof(double), stream));
+    BA_CUDA(cudaStreamSynchronize(stream));
+    p2p = okd > 0.5;
+    px.ws = opt.world_size;
+    px.rank = opt.rank;
     return BA_OK;
   }
 
@@ -503,7 +566,13 @@ struct ImplT : Impl {
     size_t ev_s = 0, ev_p = 0;
     if (timing) ev_s = ev_begin();
     const bool multi = opt.world_size > 1;
-    const int nrep = multi ? 1 : NREP;  // multi-GPU: replicas are folded before the allreduce
+    // multi-GPU: either the fused peer-memory exchange inside the camera kernel, or fold + NCCL allreduce
+    static const bool no_p2p_env = getenv("BA_NO_P2P") != nullptr;
+    const bool fused = multi && p2p && !no_p2p_env && pcg_reg_kernel_available<T>(d);
+    const int nrep = (multi && !fused) ? 1 : NREP;
+    PeerExchange pxl = px;
+    if (!fused) pxl.ws = 1;
+    auto next_epoch = [&]() { if (fused) { pxl.epoch = ++px_epoch; pxl.parity = (int)(px_epoch & 1); } };
     BA_CUDA(cudaMemsetAsync(d.sA, 0, sizeof(T) * 3 * NREP * 9 * g.nC, stream));
     const size_t set_sz = (size_t)NREP * 9 * g.nC;  // sB set k lives at d.sB + k * set_sz
     BA_CUDA(launch_prep<T>(d, stream));
@@ -512,13 +581,14 @@ struct ImplT : Impl {
     BA_CUDA(launch_pad_cam<T>(d, d.dxc, stream));
     stats.launches += 1;
     BA_TRY(schur_edge(SM_FULL, d.xpad, d.sB, 0, true));     // sB = Hpl Hll^-1 Hlp x0
-    if (multi) {
+    if (multi && !fused) {
       BA_CUDA(launch_fold_replicas<T>(d, d.sA, 2, stream));
       stats.launches += 1;
       BA_TRY(allreduce_T(d.sA, 9 * (size_t)g.nC));
       BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
     }
-    BA_CUDA(launch_pcg_init<T>(d, d.sB, o->max_iter, o->tol, o->refuse_ratio, nrep, stream));
+    next_epoch();
+    BA_CUDA(launch_pcg_init<T>(d, d.sB, o->max_iter, o->tol, o->refuse_ratio, nrep, pxl, stream));
     stats.launches += 1;
     if (timing) ev_p = ev_begin();
     // The loop is enqueued in chunks; the device-side `active` flag turns the remaining launches of a
@@ -550,14 +620,15 @@ struct ImplT : Impl {
         const int it = launched + i;
         T *cur = d.sB + (size_t)((it + 1) & 1) * set_sz, *other = d.sB + (size_t)(it & 1) * set_sz;
         BA_TRY(schur_edge(SM_FULL, d.xpad, cur, 1, true, other));  // xpad holds p (written by the camera kernel)
-        if (multi) {
+        if (multi && !fused) {
           BA_CUDA(launch_fold_replicas<T>(d, cur, 1, stream));
           stats.launches += 1;
           BA_TRY(allreduce_T(cur, 9 * (size_t)g.nC));
         }
+        next_epoch();
         size_t evc = 0;
         if (timing) evc = ev_begin();
-        BA_CUDA(launch_pcg_step<T>(d, cur, nrep, stream));
+        BA_CUDA(launch_pcg_step<T>(d, cur, nrep, pxl, stream));
         if (timing) { ev_end(evc); ev_cam.push_back(evc); }
         stats.launches += 1;
       }
@@ -572,7 +643,9 @@ struct ImplT : Impl {
     {
       // final state (also covers max_iter <= 0 and the over-enqueued chunk)
       BA_CUDA(cudaMemcpyAsync(&h_st[0], d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+      BA_CUDA(cudaMemcpyAsync(h_scal + S_XCHG_ERR, d.scal + S_XCHG_ERR, sizeof(double), cudaMemcpyDeviceToHost, stream));
       BA_CUDA(cudaStreamSynchronize(stream));
+      if (h_scal[S_XCHG_ERR] != 0.) return fail(BA_ERR_NCCL, "peer-memory exchange timed out (a rank did not arrive)");
     }
     if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); }
     // inactive edge launches return immediately; only executed iterations are counted
@@ -841,7 +914,7 @@ int ba_comm_init(ba_solver *s, const void *id128) {
   ncclResult_t r = ncclCommInitRank(&m->comm, m->opt.world_size, id, m->opt.rank);
   if (r != ncclSuccess) return m->fail(BA_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
   m->comm_ready = true;
-  return BA_OK;
+  return m->setup_p2p();
 }
 
 #define BA_FWD(call) \

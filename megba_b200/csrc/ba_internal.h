@@ -34,9 +34,19 @@ struct PcgState {
   int n, max_iter, active, done, refused, pad;
 };
 
+// Peer-memory exchange descriptor of the fused allreduce inside the camera-space PCG kernel (world_size > 1).
+// data[r] -> rank r's exchange buffer [2 parity][2 vectors][9nC] (IPC-mapped for r != rank), flag[r] -> its two
+// 64-bit epoch flags.  ws == 1 disables the exchange.
+struct PeerExchange {
+  void *data[8];
+  unsigned long long *flag[8];
+  unsigned long long epoch;
+  int ws, rank, parity, pad;
+};
+
 // device scalar slots (double) read back by the host
 enum Scal { S_COST = 0, S_TRIAL_COST = 1, S_MODEL_SQ = 2, S_DX2_PT = 3, S_X2_PT = 4, S_DX2_CAM = 5,
-            S_X2_CAM = 6, S_GINF = 7, S_COUNT = 16 };
+            S_X2_CAM = 6, S_GINF = 7, S_XCHG_ERR = 15, S_COUNT = 16 };
 
 template <typename T>
 struct Dev {
@@ -85,8 +95,10 @@ enum SchurMode { SM_FULL = 0, SM_MAKEV = 1, SM_BACKSUB = 2 };
 template <typename T> cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set,
                                                     int check_active, cudaStream_t st);
 template <typename T> cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st);
-template <typename T> cudaError_t launch_pcg_init(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep, cudaStream_t st);
-template <typename T> cudaError_t launch_pcg_step(const Dev<T> &d, T *sB, int nrep, cudaStream_t st);
+template <typename T> cudaError_t launch_pcg_init(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep,
+                                                  const PeerExchange &px, cudaStream_t st);
+template <typename T> cudaError_t launch_pcg_step(const Dev<T> &d, T *sB, int nrep, const PeerExchange &px, cudaStream_t st);
+template <typename T> bool pcg_reg_kernel_available(const Dev<T> &d);
 template <typename T> cudaError_t launch_fold_replicas(const Dev<T> &d, T *s, int nvec, cudaStream_t st);
 template <typename T> cudaError_t launch_pad_cam(const Dev<T> &d, const T *src, cudaStream_t st);
 int pcg_cluster_size();

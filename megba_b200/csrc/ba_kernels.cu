@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, T *sB, int ma
 // vectors and keeps their Hpp / Hpp^-1 rows, p, r, x in registers for the whole kernel, so the kernel
 // is one L2 round trip + two cluster reductions instead of a chain of dependent global round trips.
 template <typename T, int INIT, int RPT, bool PRE_INV>
-__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const T *__restrict__ sB, int max_iter, double tol, double refuse, int nrep) {
+__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const T *__restrict__ sB, int max_iter, double tol, double refuse, int nrep, PeerExchange px) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red_warp[32];
@@ -768,17 +768,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
     st = *d.st;
     if (!st.active) return;
   }
-  const int cut = nrep >> 8;
-  nrep &= 255;
   const int ncta = cl.num_blocks(), rank = cl.block_rank();
-#define BA_CUT(k, dep)                                                        \
-  if (!INIT && cut == k) {                                                    \
-    if (rank == 0 && threadIdx.x == 0) {                                      \
-      st.n += 1; st.active = st.n < st.max_iter; st.rho = 1. + 1e-300 * (double)(dep); *d.st = st; \
-    }                                                                         \
-    return;                                                                   \
-  }
-  BA_CUT(1, 0)
   const int per = (d.nC + ncta - 1) / ncta;
   const int c0 = min(d.nC, rank * per), c1 = min(d.nC, c0 + per);
   const int i0 = 9 * c0, nrows = 9 * (c1 - c0);
@@ -813,10 +803,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
 #pragma unroll
       for (int rep = 0; rep < NREP; ++rep) sb += sbv[rep];
       sj[j] = sb;
+      T sa = T(0);
       if (INIT) {
 #pragma unroll
         for (int rep = 0; rep < NREP; ++rep) sbv[rep] = rep < nrep ? d.sA[rep * rs + i] : T(0);
-        T sa = T(0);
 #pragma unroll
         for (int rep = 0; rep < NREP; ++rep) sa += sbv[rep];
         pj[j] = xj[j];               // operand of Hpp x0
@@ -826,9 +816,48 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
         rj[j] = d.r[i];
       }
       p_s[l] = pj[j];
+      if (px.ws > 1) {  // publish this rank's partial sums for the peers (own HBM, read by them over NVLink)
+        T *mine = reinterpret_cast<T *>(px.data[px.rank]) + (size_t)px.parity * 2 * rs;
+        mine[i] = sb;
+        if (INIT) mine[rs + i] = sa;
+      }
     }
   }
   if (!PRE_INV) cp_async_commit();
+  if (px.ws > 1) {
+    // ---- fused allreduce over NVLink peer memory (replaces fold kernel + ncclAllReduce + a launch):
+    // every rank publishes its partial camera vector, raises a flag, waits for all flags, and sums the
+    // ws partials in rank order -- the same order on every rank, so the result is bit-identical everywhere.
+    __threadfence_system();
+    cl.sync();
+    if (rank == 0 && tid == 0)
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flag[px.rank] + px.parity), "l"(px.epoch) : "memory");
+    if (tid < px.ws) {
+      const unsigned long long *f = px.flag[tid] + px.parity;
+      unsigned long long v = 0;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      } while (v < px.epoch && clock64() - t0 < 4000000000ll);  // ~2 s guard: never hang the GPU
+      if (v < px.epoch) d.scal[S_XCHG_ERR] = 1.;  // surfaced to the host as BA_ERR_NCCL
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PCG_THREADS;
+      if (l < nrows) {
+        const int i = i0 + l;
+        T sb = T(0), sa = T(0);
+        for (int r = 0; r < px.ws; ++r) {
+          const T *peer = reinterpret_cast<const T *>(px.data[r]) + (size_t)px.parity * 2 * rs;
+          sb += __ldcv(peer + i);
+          if (INIT) sa += __ldcv(peer + rs + i);
+        }
+        sj[j] = sb;
+        if (INIT) rj[j] = d.gc[i] - sa;
+      }
+    }
+  }
   __syncthreads();
   double acc = 0.;
 #pragma unroll
@@ -844,10 +873,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
       else acc += (double)(pj[j] * qj[j]);
     }
   }
-  BA_CUT(2, acc)
   if (!INIT) {
     const double pq = cluster_sum(acc, red_warp, &slots[0], cl);
-    BA_CUT(3, pq)
     const T alpha = (T)(st.rho / pq);          // :385
     st.alpha = (double)alpha; st.pq = pq;
 #pragma unroll
@@ -880,9 +907,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
       acc += (double)(rj[j] * a);
     }
   }
-  BA_CUT(4, acc)
   const double rho_new = (double)(T)cluster_sum(acc, red_warp, &slots[1], cl);
-  BA_CUT(5, rho_new)
   bool cont = true, refused = false;
   if (!INIT) {
     st.n += 1;                                 // :405
@@ -1153,9 +1178,9 @@ cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, 
   return cudaGetLastError();
 }
 
-template <typename K, typename T, typename P>
+template <typename K, typename T, typename P, typename... X>
 static cudaError_t launch_cluster(K kernel, int cl, size_t smem, const Dev<T> &d, P sB, int max_iter, double tol,
-                                  double refuse, int nrep, cudaStream_t st) {
+                                  double refuse, int nrep, cudaStream_t st, X... extra) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cl);
   cfg.blockDim = dim3(PCG_THREADS);
@@ -1168,12 +1193,12 @@ static cudaError_t launch_cluster(K kernel, int cl, size_t smem, const Dev<T> &d
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, d, sB, max_iter, tol, refuse, nrep);
+  return cudaLaunchKernelEx(&cfg, kernel, d, sB, max_iter, tol, refuse, nrep, extra...);
 }
 
 template <typename T, int INIT, int RPT>
 static cudaError_t launch_pcg_reg(const Dev<T> &d, T *sB, int cl, int max_iter, double tol, double refuse, int nrep,
-                                  cudaStream_t st) {
+                                  const PeerExchange &px, cudaStream_t st) {
   constexpr bool PRE = RPT <= 1 || sizeof(T) == 4;
   auto kern = k_pcg_cam_reg<T, INIT, RPT, PRE>;
   const size_t smem = (2 + (PRE ? 0 : 9)) * (size_t)RPT * PCG_THREADS * sizeof(T);
@@ -1183,7 +1208,7 @@ static cudaError_t launch_pcg_reg(const Dev<T> &d, T *sB, int cl, int max_iter, 
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prepared = true;
   }
-  return launch_cluster(kern, cl, smem, d, (const T *)sB, max_iter, tol, refuse, nrep, st);
+  return launch_cluster(kern, cl, smem, d, (const T *)sB, max_iter, tol, refuse, nrep, st, px);
 }
 
 // 16-CTA clusters are "non-portable": ask the occupancy API once whether this device can host one.
@@ -1212,27 +1237,36 @@ int pcg_cluster_size() {
 }
 
 template <typename T, int INIT>
-static cudaError_t launch_pcg_cam(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep, cudaStream_t st) {
-  static int clenv = -1, cut = 0;
-  if (clenv < 0) { const char *e = getenv("BA_CL"); clenv = e ? atoi(e) : 0; e = getenv("BA_CAMCUT"); cut = e ? atoi(e) : 0; }
-  nrep |= cut << 8;
+static cudaError_t launch_pcg_cam(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep,
+                                  const PeerExchange &px, cudaStream_t st) {
+  static int clenv = -1;
+  if (clenv < 0) { const char *e = getenv("BA_CL"); clenv = e ? atoi(e) : 0; }
   const int cl = clenv ? clenv : pcg_cluster_size();
   const int rows = 9 * ((d.nC + cl - 1) / cl);
   const int rpt = (rows + PCG_THREADS - 1) / PCG_THREADS;
-  if (rpt <= 1) return launch_pcg_reg<T, INIT, 1>(d, sB, cl, max_iter, tol, refuse, nrep, st);
-  if (rpt <= 2) return launch_pcg_reg<T, INIT, 2>(d, sB, cl, max_iter, tol, refuse, nrep, st);
-  if (rpt <= 4) return launch_pcg_reg<T, INIT, 4>(d, sB, cl, max_iter, tol, refuse, nrep, st);
-  if (rpt <= 8) return launch_pcg_reg<T, INIT, 8>(d, sB, cl, max_iter, tol, refuse, nrep, st);
+  if (rpt <= 1) return launch_pcg_reg<T, INIT, 1>(d, sB, cl, max_iter, tol, refuse, nrep, px, st);
+  if (rpt <= 2) return launch_pcg_reg<T, INIT, 2>(d, sB, cl, max_iter, tol, refuse, nrep, px, st);
+  if (rpt <= 4) return launch_pcg_reg<T, INIT, 4>(d, sB, cl, max_iter, tol, refuse, nrep, px, st);
+  if (rpt <= 8) return launch_pcg_reg<T, INIT, 8>(d, sB, cl, max_iter, tol, refuse, nrep, px, st);
+  if (px.ws > 1) return cudaErrorNotSupported;  // callers fall back to fold + NCCL before reaching this
   return launch_cluster(k_pcg_cam<T, INIT>, PCG_CL, 0, d, sB, max_iter, tol, refuse, nrep, st);
 }
 
 template <typename T>
-cudaError_t launch_pcg_init(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep, cudaStream_t st) {
-  return launch_pcg_cam<T, 1>(d, sB, max_iter, tol, refuse, nrep, st);
+cudaError_t launch_pcg_init(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep,
+                            const PeerExchange &px, cudaStream_t st) {
+  return launch_pcg_cam<T, 1>(d, sB, max_iter, tol, refuse, nrep, px, st);
 }
 template <typename T>
-cudaError_t launch_pcg_step(const Dev<T> &d, T *sB, int nrep, cudaStream_t st) {
-  return launch_pcg_cam<T, 0>(d, sB, 0, 0., 0., nrep, st);
+cudaError_t launch_pcg_step(const Dev<T> &d, T *sB, int nrep, const PeerExchange &px, cudaStream_t st) {
+  return launch_pcg_cam<T, 0>(d, sB, 0, 0., 0., nrep, px, st);
+}
+// true when the register-resident camera kernel (the only one with the fused peer exchange) covers this size
+template <typename T>
+bool pcg_reg_kernel_available(const Dev<T> &d) {
+  const int cl = pcg_cluster_size();
+  const int rows = 9 * ((d.nC + cl - 1) / cl);
+  return (rows + PCG_THREADS - 1) / PCG_THREADS <= 8;
 }
 
 template <typename T>
@@ -1291,8 +1325,9 @@ cudaError_t launch_cam_matvec_sub(const Dev<T> &d, const T *p, const T *s, T *q,
   template cudaError_t launch_linearize<T>(const Dev<T> &, cudaStream_t);                                   \
   template cudaError_t launch_schur_edge<T>(const Dev<T> &, int, const T *, T *, T *, int, cudaStream_t);   \
   template cudaError_t launch_prep<T>(const Dev<T> &, cudaStream_t);                                        \
-  template cudaError_t launch_pcg_init<T>(const Dev<T> &, T *, int, double, double, int, cudaStream_t);     \
-  template cudaError_t launch_pcg_step<T>(const Dev<T> &, T *, int, cudaStream_t);                          \
+  template cudaError_t launch_pcg_init<T>(const Dev<T> &, T *, int, double, double, int, const PeerExchange &, cudaStream_t); \
+  template cudaError_t launch_pcg_step<T>(const Dev<T> &, T *, int, const PeerExchange &, cudaStream_t);    \
+  template bool pcg_reg_kernel_available<T>(const Dev<T> &);                                                \
   template cudaError_t launch_fold_replicas<T>(const Dev<T> &, T *, int, cudaStream_t);                     \
   template cudaError_t launch_pad_cam<T>(const Dev<T> &, const T *, cudaStream_t);                          \
   template cudaError_t launch_trial<T>(const Dev<T> &, cudaStream_t);                                       \
