@@ -88,13 +88,15 @@ typedef struct {
   int64_t lm_iters;          /* LM iterations executed (accepted + rejected)     */
   int64_t pcg_iters;         /* PCG iterations executed (n of schur_pcg :405)    */
   int64_t schur_apply_calls; /* launches of the S*p edge kernel                  */
-  double schur_apply_ms;     /* summed device time of those launches (timing on) */
+  double schur_apply_ms;     /* summed device time of the TIMED launches (timing on) */
   int64_t linearize_calls;
   double linearize_ms;       /* summed device time of ba_linearize (timing on)   */
   double pcg_loop_ms;        /* device time inside the PCG do-while bodies       */
   double solve_ms;           /* device time of ba_solve (inverse+MakeV+PCG+SolveW)*/
-  double pcg_cam_ms;         /* summed device time of the camera-space PCG kernel (all launches)   */
-  double reserved[3];
+  double pcg_cam_ms;         /* summed device time of the TIMED camera-space PCG kernel launches   */
+  double schur_apply_timed;  /* how many S*p launches carry an event pair (see ba_set_timing)      */
+  double pcg_cam_timed;      /* same for the camera-space kernel                                   */
+  double reserved[1];
 } ba_stats;
 
 typedef struct ba_solver ba_solver;
@@ -201,6 +203,8 @@ int ba_eval_edges(ba_solver *s, void *r, void *J);
  * one operator application of the PCG loop (schur_pcg_solver.cu:315-366).          */
 int ba_schur_apply(ba_solver *s, const void *p, void *q);
 
+/* on = 0: no events.  on = 1: CUDA-event pair around every hot-kernel launch.  on = N > 1: around the launches of
+ * every N-th PCG iteration only (sampling keeps the event overhead out of the measured throughput).              */
 int ba_set_timing(ba_solver *s, int32_t on);
 int ba_reset_stats(ba_solver *s);
 int ba_get_stats(ba_solver *s, ba_stats *out);

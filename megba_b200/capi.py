@@ -55,7 +55,7 @@ class Stats(C.Structure):
                 ("schur_apply_calls", C.c_int64), ("schur_apply_ms", C.c_double),
                 ("linearize_calls", C.c_int64), ("linearize_ms", C.c_double),
                 ("pcg_loop_ms", C.c_double), ("solve_ms", C.c_double), ("pcg_cam_ms", C.c_double),
-                ("reserved", C.c_double * 3)]
+                ("schur_apply_timed", C.c_double), ("pcg_cam_timed", C.c_double), ("reserved", C.c_double * 1)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -251,7 +251,8 @@ class Solver:
         self._chk(self.L.ba_schur_apply(self.h, _p(p), _p(q)), "ba_schur_apply")
         return q
 
-    def set_timing(self, on: bool):
+    def set_timing(self, on):
+        """0/False off, 1/True every launch, N > 1 every N-th PCG iteration."""
         self._chk(self.L.ba_set_timing(self.h, int(on)), "ba_set_timing")
 
     def reset_stats(self):

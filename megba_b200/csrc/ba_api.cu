@@ -193,6 +193,7 @@ struct Impl {
   ncclComm_t comm = nullptr;
   bool comm_ready = false;
   bool timing = false;
+  int timing_stride = 1;  // per-launch events are recorded for every timing_stride-th PCG iteration
   ba_stats stats{};
   bool linearized = false, have_step = false;
   double region = 1e3;
@@ -290,6 +291,8 @@ struct ImplT : Impl {
   }
   void fold_events() {
     cudaStreamSynchronize(stream);
+    stats.schur_apply_timed += (double)ev_schur.size();
+    stats.pcg_cam_timed += (double)ev_cam.size();
     stats.schur_apply_ms += ev_sum(ev_schur);
     stats.linearize_ms += ev_sum(ev_lin);
     stats.pcg_loop_ms += ev_sum(ev_pcg);
@@ -577,10 +580,12 @@ struct ImplT : Impl {
     const size_t set_sz = (size_t)NREP * 9 * g.nC;  // sB set k lives at d.sB + k * set_sz
     BA_CUDA(launch_prep<T>(d, stream));
     stats.launches += launches_of_prep();
-    BA_TRY(schur_edge(SM_MAKEV, nullptr, d.sA, 0, false));  // sA = Hpl w
+    // MakeV and the operator application on the warm start x0 share ONE pass over W:
+    //   sB = Hpl (Hll^-1 Hlp x0 - w)  so that  r0 = v - S x0 = g_c - Hpp x0 + sB   (schur_pcg_solver.cu:430-510,202-258);
+    // sA (the reference's separate Hpl w) stays zero.
     BA_CUDA(launch_pad_cam<T>(d, d.dxc, stream));
     stats.launches += 1;
-    BA_TRY(schur_edge(SM_FULL, d.xpad, d.sB, 0, true));     // sB = Hpl Hll^-1 Hlp x0
+    BA_TRY(schur_edge(SM_INIT, d.xpad, d.sB, 0, true));
     if (multi && !fused) {
       BA_CUDA(launch_fold_replicas<T>(d, d.sA, 2, stream));
       stats.launches += 1;
@@ -595,31 +600,28 @@ struct ImplT : Impl {
     // chunk into no-ops once the reference's do-while would have exited.  The state of chunk k is polled
     // only after chunk k+1 has been enqueued, so the GPU never waits for the host.
     int launched = 0, n_seen = 0, chunk_id = 0;
-    struct Pending { size_t ev_mark, evc_mark; int slot; bool valid; } pend{0, 0, 0, false};
+    struct Pending { int slot; bool valid; } pend{0, false};
+    std::vector<std::pair<size_t, int>> loc_schur, loc_cam;  // (event pair, iteration) of the sampled launches
     bool finished = false;
     auto poll = [&](const Pending &pd) -> int {
       BA_CUDA(cudaEventSynchronize(st_event[pd.slot]));
       const PcgState &hs = h_st[pd.slot];
-      if (!hs.active) {
-        // launches issued after the loop ended returned immediately: keep only the event pairs of the
-        // iterations that really ran (this also drops the pairs of an over-enqueued later chunk)
-        if (timing) {
-          ev_schur.resize(pd.ev_mark + (size_t)(hs.n - n_seen));
-          ev_cam.resize(pd.evc_mark + (size_t)(hs.n - n_seen));
-        }
-        finished = true;
-      }
+      if (!hs.active) finished = true;
       n_seen = hs.n;
       return BA_OK;
     };
     while (launched < o->max_iter && !finished) {
       const int n = std::min(pcg_chunk, o->max_iter - launched);
-      const size_t ev_mark = ev_schur.size(), evc_mark = ev_cam.size();
       for (int i = 0; i < n; ++i) {
         // iteration it accumulates into set (it+1)&1 and clears set it&1 (read by the previous camera kernel)
         const int it = launched + i;
         T *cur = d.sB + (size_t)((it + 1) & 1) * set_sz, *other = d.sB + (size_t)(it & 1) * set_sz;
-        BA_TRY(schur_edge(SM_FULL, d.xpad, cur, 1, true, other));  // xpad holds p (written by the camera kernel)
+        const bool sample = timing && (it % timing_stride) == 0;
+        size_t eve = 0;
+        if (sample) eve = ev_begin();
+        BA_TRY(schur_edge(SM_FULL, d.xpad, cur, 1, false, other));  // xpad holds p (written by the camera kernel)
+        if (sample) { ev_end(eve); loc_schur.push_back({eve, it}); }
+        stats.schur_apply_calls += 1;
         if (multi && !fused) {
           BA_CUDA(launch_fold_replicas<T>(d, cur, 1, stream));
           stats.launches += 1;
@@ -627,9 +629,9 @@ struct ImplT : Impl {
         }
         next_epoch();
         size_t evc = 0;
-        if (timing) evc = ev_begin();
+        if (sample) evc = ev_begin();
         BA_CUDA(launch_pcg_step<T>(d, cur, nrep, pxl, stream));
-        if (timing) { ev_end(evc); ev_cam.push_back(evc); }
+        if (sample) { ev_end(evc); loc_cam.push_back({evc, it}); }
         stats.launches += 1;
       }
       launched += n;
@@ -637,7 +639,7 @@ struct ImplT : Impl {
       BA_CUDA(cudaMemcpyAsync(&h_st[slot], d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
       BA_CUDA(cudaEventRecord(st_event[slot], stream));
       if (pend.valid) BA_TRY(poll(pend));
-      pend = Pending{ev_mark, evc_mark, slot, true};
+      pend = Pending{slot, true};
     }
     if (pend.valid && !finished) BA_TRY(poll(pend));
     {
@@ -650,6 +652,9 @@ struct ImplT : Impl {
     if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); }
     // inactive edge launches return immediately; only executed iterations are counted
     stats.schur_apply_calls -= (launched - h_st[0].n);
+    // launches issued after the loop ended returned immediately: keep only the samples of iterations that ran
+    for (auto &e : loc_schur) if (e.second < h_st[0].n) ev_schur.push_back(e.first);
+    for (auto &e : loc_cam) if (e.second < h_st[0].n) ev_cam.push_back(e.first);
     BA_CUDA(launch_pad_cam<T>(d, d.dxc, stream));
     stats.launches += 1;
     BA_TRY(schur_edge(SM_BACKSUB, d.xpad, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
@@ -943,6 +948,7 @@ int ba_algorithmic_bytes(ba_solver *s, double *a, double *b) { BA_FWD(algorithmi
 int ba_set_timing(ba_solver *s, int32_t on) {
   if (!s) return BA_ERR_ARG;
   s->impl->timing = on != 0;
+  s->impl->timing_stride = on > 1 ? on : 1;
   return BA_OK;
 }
 

@@ -91,7 +91,7 @@ struct Dev {
 
 // ---- launchers (ba_kernels.cu); all enqueue on `st` and return cudaGetLastError ----
 template <typename T> cudaError_t launch_linearize(const Dev<T> &d, cudaStream_t st);
-enum SchurMode { SM_FULL = 0, SM_MAKEV = 1, SM_BACKSUB = 2 };
+enum SchurMode { SM_FULL = 0, SM_MAKEV = 1, SM_BACKSUB = 2, SM_INIT = 3 };
 template <typename T> cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set,
                                                     int check_active, cudaStream_t st);
 template <typename T> cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st);

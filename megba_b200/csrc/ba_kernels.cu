@@ -541,6 +541,10 @@ __global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restr
         for (int k = 0; k < 9; ++k) hi[k] = PREF ? hv[9 * tid + k] : __ldg(d.HllInv + 9 * (size_t)p + k);
 #pragma unroll
         for (int y = 0; y < 3; ++y) u[y] = hi[3 * y] * t0 + hi[3 * y + 1] * t1 + hi[3 * y + 2] * t2;
+        if (MODE == SM_INIT) {  // u = Hll^-1 Hlp x0 - w: one pass yields  Hpl Hll^-1 Hlp x0 - Hpl w
+#pragma unroll
+          for (int y = 0; y < 3; ++y) u[y] -= PREF ? hw[3 * tid + y] : d.w[3 * (size_t)p + y];
+        }
         if (MODE == SM_BACKSUB) {
 #pragma unroll
           for (int y = 0; y < 3; ++y) d.dxl[3 * (size_t)p + y] = (PREF ? hw[3 * tid + y] : d.w[3 * (size_t)p + y]) - u[y];
@@ -584,6 +588,10 @@ __global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restr
       for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInv + 9 * (size_t)pt0 + k);
 #pragma unroll
       for (int y = 0; y < 3; ++y) u[y] = hi[3 * y] * t0 + hi[3 * y + 1] * t1 + hi[3 * y + 2] * t2;
+      if (MODE == SM_INIT) {
+#pragma unroll
+        for (int y = 0; y < 3; ++y) u[y] -= d.w[3 * (size_t)pt0 + y];
+      }
       if (MODE == SM_BACKSUB) {
         if (tid == 0) {
 #pragma unroll
@@ -1166,6 +1174,7 @@ static void launch_schur_edge_t(const Dev<T> &d, int mode, const T *xin, T *sout
   switch (mode) {
     case SM_FULL: launch_schur_edge_m<T, IMPLICIT, SM_FULL>(d, xin, sout, zero_set, check_active, st); break;
     case SM_MAKEV: launch_schur_edge_m<T, IMPLICIT, SM_MAKEV>(d, xin, sout, zero_set, check_active, st); break;
+    case SM_INIT: launch_schur_edge_m<T, IMPLICIT, SM_INIT>(d, xin, sout, zero_set, check_active, st); break;
     default: launch_schur_edge_m<T, IMPLICIT, SM_BACKSUB>(d, xin, sout, zero_set, check_active, st); break;
   }
 }

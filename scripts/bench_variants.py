@@ -27,10 +27,19 @@ def child():
         S.solve(max_iter=40, tol=0.0, refuse_ratio=1e300)
     st = S.stats()
     a_pcg, _ = S.algorithmic_bytes()
-    k = st["schur_apply_ms"] / st["schur_apply_calls"]
+    k = st["schur_apply_ms"] / st["schur_apply_timed"]
     print(f"VAR={os.environ.get('BA_VAR','-')} edge {k*1e3:8.1f} us  {a_pcg/k/1e6:7.0f} GB/s   pcg loop "
-          f"{st['pcg_loop_ms']/st['pcg_iters']*1e3:7.1f} us/iter   cam kernel {st['pcg_cam_ms']/st['pcg_iters']*1e3:6.1f} us   "
+          f"{st['pcg_loop_ms']/st['pcg_iters']*1e3:7.1f} us/iter   cam kernel {st['pcg_cam_ms']/max(st['pcg_cam_timed'],1)*1e3:6.1f} us   "
           f"solve {st['solve_ms']/3:7.2f} ms", flush=True)
+    # same three solves without per-launch events: host wall clock around the (synchronous) call
+    import time
+    S.set_timing(False)
+    S.solve(max_iter=40, tol=0.0, refuse_ratio=1e300)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        S.solve(max_iter=40, tol=0.0, refuse_ratio=1e300)
+    dt = (time.perf_counter() - t0) / 3
+    print(f"        timing off: solve {dt*1e3:7.2f} ms wall  (vs {st['solve_ms']/3:7.2f} ms with per-launch events)", flush=True)
 
 
 if __name__ == "__main__":
