@@ -85,7 +85,7 @@ __device__ __forceinline__ void left_factor(const T *J, const T *info4, T *L) {
 // --------------------------------------------------------------------------------
 // HP1-A: point-major linearisation.  One CTA per tile, one thread per slot.
 template <typename T, bool IMPLICIT>
-__global__ void __launch_bounds__(TE) k_lin_pm(Dev<T> d) {
+__global__ void __launch_bounds__(TE, 3) k_lin_pm(Dev<T> d) {
   constexpr int K = IMPLICIT ? 24 : 27;
   __shared__ T sh[12][TE];
   __shared__ double red[32];
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TE) k_lin_pm(Dev<T> d) {
 // (camera, chunk of <= CM_CHUNK edges); residual/Jacobian are recomputed from the
 // L2-resident point array instead of being re-read from HBM.
 template <typename T>
-__global__ void __launch_bounds__(CM_THREADS) k_lin_cm(Dev<T> d) {
+__global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm(Dev<T> d) {
   constexpr int NW = CM_THREADS / 32;
   __shared__ T sh[NW][NTRI + 9];
   const int4 ch = d.chunk[blockIdx.x];
@@ -979,7 +979,7 @@ __global__ void __launch_bounds__(256) k_fold_replicas(T *s, int n, int nvec, si
 // --------------------------------------------------------------------------------
 // LM scalars
 template <typename T>
-__global__ void __launch_bounds__(TE) k_trial(Dev<T> d) {
+__global__ void __launch_bounds__(TE, 3) k_trial(Dev<T> d) {
   __shared__ double red[32];
   const int4 td = d.tile[blockIdx.x];
   const int slot0 = td.x, ne = td.y, pt0 = td.z;

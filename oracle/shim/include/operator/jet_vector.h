@@ -52,6 +52,7 @@ class Matrix {
   void resize(long r, long c) { r_ = r; c_ = c; v_.assign((std::size_t)(r * c), S{}); }
   long rows() const { return r_; }
   long cols() const { return c_; }
+  long size() const { return r_ * c_; }
   S &operator()(long i) { return v_[i]; }
   const S &operator()(long i) const { return v_[i]; }
   S &operator()(long i, long j) { return v_[(std::size_t)(j * r_ + i)]; }

@@ -9,6 +9,7 @@ class MemoryPool {
   static void resetPool(const ProblemOption *o) { _problemOption = o; }
   static void allocateNormal(void **ptr, size_t size, int rank = 0);
   static void deallocateNormal(void *ptr, int rank = 0);
+  static void redistribute() {}
   static std::size_t getWorldSize() { return _problemOption->deviceUsed.size(); }
   // same partition rule as the reference (include/resource/memory_pool.h:48-63)
   static std::size_t getItemNum(int rank) { return getItemNum(rank, (std::size_t)_problemOption->nItem); }
