@@ -17,13 +17,13 @@
  *
  * Pinning: upstream ships no tests, golden vectors or fixtures for this path and has no CPU execution path, so it
  * cannot be run here as a whole.  The oracle is pinned by
- *   (i)  the reference's own CUDA sources for rows a2, a3, a5-a8 (analytical_derivatives.cu, build_linear_system.cu,
- *        schur_pcg_solver.cu) compiled UNMODIFIED against shim headers into oracle/_ref/ (oracle/shim/README.md) and
- *        run on the GPU box by tests/test_gpu_reference_pin.py against this oracle and against the product;
+ *   (i)  the reference's own CUDA sources for rows a2-a8, a10, a11 (analytical_derivatives.cu, build_linear_system.cu,
+ *        schur_pcg_solver.cu, schur_LM_linear_system.cu, lm_algo.cu/.cpp -- i.e. its whole LM loop) compiled
+ *        UNMODIFIED against shim headers into oracle/_ref/ (oracle/shim/README.md) and run on the GPU box by
+ *        tests/test_gpu_reference_pin.py against this oracle and against the product;
  *   (ii) independent mathematics in tests/test_oracle.py (central finite differences on J, dense normal-equation
  *        solve vs PCG, independent projection, cost monotonicity).
- * PARITY UNPINNED for a4 (damping), a10 (LM scalars) and the a11 control law: those are restatements checked only
- * by (ii) and by end-to-end LM traces.
+ * Nothing on the path is left pinned by restatement alone except the trivial per-edge parameter update (a9).
  */
 #include <math.h>
 #include <stdint.h>
