@@ -403,26 +403,6 @@ __device__ __forceinline__ void warp_scatter9(T *sv, int *sc, const T *o, int c,
   __syncwarp();
 }
 
-// Camera-side gather, the mirror image of warp_scatter9: lanes read consecutive components of one
-// camera (a few 32 B sectors per instruction instead of 32 different lines), stage them in shared
-// memory and each lane then picks up the 9 values of its own observation.
-template <typename T>
-__device__ __forceinline__ const T *warp_gather9(T *sv, int *sc, const T *__restrict__ xin, int c) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  T *mine = sv + (size_t)w * 32 * 9;
-  int *cams = sc + w * 32;
-  cams[lane] = c;
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    const int v = j * 32 + lane, el = v / 9, k = v - 9 * el;
-    const int cc = cams[el];
-    mine[v] = cc >= 0 ? __ldg(xin + 9 * (size_t)cc + k) : T(0);
-  }
-  __syncwarp();
-  return mine + lane * 9;  // this lane's 9 values (stride 9 scalars: bank-conflict free)
-}
-
 // Camera-space vectors consumed by the edge kernel are kept in a padded copy (stride CamPad::N scalars,
 // 16-byte aligned rows) so that one lane fetches its camera's 9 values with 16-byte loads.
 template <typename T, bool VEC>
@@ -456,9 +436,10 @@ __device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// VAR bits (design-space switches kept for measurement, see profiles/):
+// VAR bits.  The shipped kernel is VAR = 5; VAR = 0 (env BA_VAR=0) is kept as the measured baseline
+// (profiles/r01_edge_variants_padded_gather.txt).
 //   1 = camera values gathered with 16-byte vector loads from the padded copy (5 instead of 9 tag lookups per lane)
-//   2 = W/J loads use the evict-first (streaming) policy
+//   2 = W/J loads use the evict-first (streaming) policy (measured: no effect; not instantiated)
 //   4 = the tile's Hll^-1 blocks / w vectors are prefetched into shared memory with cp.async at kernel start
 template <typename T, int MODE, int VAR>
 __host__ __device__ constexpr size_t schur_smem_bytes() {
@@ -466,7 +447,7 @@ __host__ __device__ constexpr size_t schur_smem_bytes() {
 }
 
 template <typename T, bool IMPLICIT, int MODE, int VAR>
-__global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active, int abl) {
+__global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
   constexpr int K = IMPLICIT ? 24 : 27;
   constexpr bool VEC = (VAR & 1) != 0, LDCS = (VAR & 2) != 0, PREF = (VAR & 4) != 0;
   if (check_active && !d.st->active) return;
@@ -517,12 +498,7 @@ __global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restr
       T t[3];
       if (valid) {
         __align__(16) T x[CamPad<T>::N];
-        if (abl & 2) {
-#pragma unroll
-          for (int k = 0; k < 9; ++k) x[k] = T(1);
-        } else {
-          gather_cam<T, VEC>(xin, c, x);
-        }
+        gather_cam<T, VEC>(xin, c, x);
         edge_t<T, IMPLICIT>(wj, x, t);
       }
       if (valid) { sh_t[tid] = t[0]; sh_t[TE + tid] = t[1]; sh_t[2 * TE + tid] = t[2]; }
@@ -534,7 +510,6 @@ __global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restr
       T u[3];
       if (MODE != SM_MAKEV) {
         T t0 = T(0), t1 = T(0), t2 = T(0);
-        if (abl & 4) { s1 = s0 + 1; }
         for (int s = s0; s < s1; ++s) { t0 += sh_t[s]; t1 += sh_t[TE + s]; t2 += sh_t[2 * TE + s]; }
         T hi[9];
 #pragma unroll
@@ -562,8 +537,7 @@ __global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restr
         const T u[3] = {sh_u[lp], sh_u[TE + lp], sh_u[2 * TE + lp]};
         edge_scatter<T, IMPLICIT>(wj, u, o);
       }
-      if (!(abl & 1)) warp_scatter9<T>(sv, sc, o, valid ? c : -1, dst);
-      else if (valid && o[0] == T(123.456)) dst[0] = o[1];
+      warp_scatter9<T>(sv, sc, o, valid ? c : -1, dst);
     }
   } else {
     // a single point with more than TE observations: two passes over its slabs (rare; simple path)
@@ -1133,12 +1107,6 @@ cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st) {
 }
 int launches_of_prep() { return 2; }
 
-static int schur_ablation() {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("BA_ABL"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
 int schur_variant() {
   static int v = -1;
   if (v < 0) {
@@ -1157,14 +1125,15 @@ static void launch_schur_edge_v(const Dev<T> &d, const T *xin, T *sout, T *zero_
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prepared = true;
   }
-  kern<<<d.nT, TE, smem, st>>>(d, xin, sout, zero_set, check_active, schur_ablation());
+  kern<<<d.nT, TE, smem, st>>>(d, xin, sout, zero_set, check_active);
 }
 
 template <typename T, bool IMPLICIT, int MODE>
 static void launch_schur_edge_m(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
   switch (schur_variant()) {
 #define BA_V(n) case n: launch_schur_edge_v<T, IMPLICIT, MODE, n>(d, xin, sout, zero_set, check_active, st); break;
-    BA_V(0) BA_V(1) BA_V(2) BA_V(3) BA_V(4) BA_V(5) BA_V(6) BA_V(7)
+    BA_V(0) BA_V(5)
+    default: launch_schur_edge_v<T, IMPLICIT, MODE, BA_DEFAULT_VAR>(d, xin, sout, zero_set, check_active, st); break;
 #undef BA_V
   }
 }
