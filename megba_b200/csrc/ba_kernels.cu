@@ -736,9 +736,47 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, T *sB, int ma
 // Register-resident variant (the one normally used): every thread owns RPT rows of the camera-space
 // vectors and keeps their Hpp / Hpp^-1 rows, p, r, x in registers for the whole kernel, so the kernel
 // is one L2 round trip + two cluster reductions instead of a chain of dependent global round trips.
-template <typename T, int INIT, int RPT, bool PRE_INV>
-__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const T *__restrict__ sB, int max_iter, double tol, double refuse, int nrep, PeerExchange px) {
+// The set of CTAs that cooperate on one camera-space PCG step: a cluster or the whole (cooperative) grid.
+template <bool GRID> struct Span;
+template <> struct Span<false> {
   cg::cluster_group cl = cg::this_cluster();
+  __device__ int num_blocks() const { return (int)cl.num_blocks(); }
+  __device__ int block_rank() const { return (int)cl.block_rank(); }
+  __device__ void sync() { cl.sync(); }
+  __device__ double sum(double v, double *red_warp, double *slot, double *) { return cluster_sum(v, red_warp, slot, cl); }
+  // peers may still read this CTA's slots: relaxed arrive/wait, so it does not wait for outstanding stores
+  __device__ void lifetime_barrier() { asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory"); }
+};
+template <> struct Span<true> {
+  cg::grid_group gr = cg::this_grid();
+  __device__ int num_blocks() const { return (int)gridDim.x; }
+  __device__ int block_rank() const { return (int)blockIdx.x; }
+  __device__ void sync() { gr.sync(); }
+  __device__ double sum(double v, double *red_warp, double *, double *partials) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum<double>(v);
+    __syncthreads();
+    if (lane == 0) red_warp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      double x = lane < nw ? red_warp[lane] : 0.;
+      x = warp_sum<double>(x);
+      if (lane == 0) partials[blockIdx.x] = x;
+    }
+    gr.sync();
+    double tot = 0.;
+    for (int r = 0; r < (int)gridDim.x; ++r) tot += __ldcg(partials + r);
+    return tot;
+  }
+  __device__ void lifetime_barrier() { gr.sync(); }  // the state word is written only after every CTA has read it
+};
+
+template <typename T, int INIT, int RPT, bool PRE_INV, bool GRID>
+__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const T *__restrict__ sB, int max_iter, double tol, double refuse, int nrep, PeerExchange px) {
+  // GRID = false: one thread-block cluster (<= 16 CTAs), reductions through distributed shared memory.
+  // GRID = true : cooperative launch over up to one CTA per SM (large camera counts), reductions through global
+  //               partials + grid barrier.  Both sum the per-CTA partials in CTA order on every CTA (deterministic).
+  Span<GRID> cl;
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red_warp[32];
   __shared__ double slots[2];
@@ -856,7 +894,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
     }
   }
   if (!INIT) {
-    const double pq = cluster_sum(acc, red_warp, &slots[0], cl);
+    const double pq = cl.sum(acc, red_warp, &slots[0], d.partials);
     const T alpha = (T)(st.rho / pq);          // :385
     st.alpha = (double)alpha; st.pq = pq;
 #pragma unroll
@@ -889,7 +927,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
       acc += (double)(rj[j] * a);
     }
   }
-  const double rho_new = (double)(T)cluster_sum(acc, red_warp, &slots[1], cl);
+  const double rho_new = (double)(T)cl.sum(acc, red_warp, &slots[1], d.partials + 512);
   bool cont = true, refused = false;
   if (!INIT) {
     st.n += 1;                                 // :405
@@ -930,7 +968,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
     }
   }
   // lifetime barrier only (peers may still read this CTA's slots): relaxed, so it does not wait for the stores above
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+  cl.lifetime_barrier();
   if (rank == 0 && tid == 0) *d.st = st;
 }
 
@@ -1178,7 +1216,7 @@ template <typename T, int INIT, int RPT>
 static cudaError_t launch_pcg_reg(const Dev<T> &d, T *sB, int cl, int max_iter, double tol, double refuse, int nrep,
                                   const PeerExchange &px, cudaStream_t st) {
   constexpr bool PRE = RPT <= 1 || sizeof(T) == 4;
-  auto kern = k_pcg_cam_reg<T, INIT, RPT, PRE>;
+  auto kern = k_pcg_cam_reg<T, INIT, RPT, PRE, false>;
   const size_t smem = (2 + (PRE ? 0 : 9)) * (size_t)RPT * PCG_THREADS * sizeof(T);
   static bool prepared = false;  // per instantiation
   if (!prepared) {
@@ -1193,7 +1231,7 @@ static cudaError_t launch_pcg_reg(const Dev<T> &d, T *sB, int cl, int max_iter, 
 int pcg_cluster_size() {
   static int cached = 0;
   if (cached) return cached;
-  auto kern = k_pcg_cam_reg<double, 0, 2, false>;
+  auto kern = k_pcg_cam_reg<double, 0, 2, false, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(16);
@@ -1214,6 +1252,32 @@ int pcg_cluster_size() {
   return cached;
 }
 
+// Cooperative-grid flavour for camera counts that do not fit one cluster at <= 2 rows per thread.
+static int pcg_grid_ctas(int nC) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int want = (9 * nC + 2 * PCG_THREADS - 1) / (2 * PCG_THREADS);
+  return want < sms ? want : sms;
+}
+
+template <typename T, int INIT, int RPT>
+static cudaError_t launch_pcg_grid(const Dev<T> &d, T *sB, int ncta, int max_iter, double tol, double refuse, int nrep,
+                                   const PeerExchange &px, cudaStream_t st) {
+  constexpr bool PRE = RPT <= 1;
+  auto kern = k_pcg_cam_reg<T, INIT, RPT, PRE, true>;
+  const size_t smem = (2 + (PRE ? 0 : 9)) * (size_t)RPT * PCG_THREADS * sizeof(T);
+  static bool prepared = false;
+  if (!prepared) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prepared = true;
+  }
+  Dev<T> dd = d;
+  const T *sBc = sB;
+  PeerExchange pxx = px;
+  void *args[] = {&dd, &sBc, &max_iter, &tol, &refuse, &nrep, &pxx};
+  return cudaLaunchCooperativeKernel((void *)kern, dim3(ncta), dim3(PCG_THREADS), args, smem, st);
+}
+
 template <typename T, int INIT>
 static cudaError_t launch_pcg_cam(const Dev<T> &d, T *sB, int max_iter, double tol, double refuse, int nrep,
                                   const PeerExchange &px, cudaStream_t st) {
@@ -1224,6 +1288,13 @@ static cudaError_t launch_pcg_cam(const Dev<T> &d, T *sB, int max_iter, double t
   const int rpt = (rows + PCG_THREADS - 1) / PCG_THREADS;
   if (rpt <= 1) return launch_pcg_reg<T, INIT, 1>(d, sB, cl, max_iter, tol, refuse, nrep, px, st);
   if (rpt <= 2) return launch_pcg_reg<T, INIT, 2>(d, sB, cl, max_iter, tol, refuse, nrep, px, st);
+  {
+    const int ncta = pcg_grid_ctas(d.nC);
+    const int grpt = (9 * ((d.nC + ncta - 1) / ncta) + PCG_THREADS - 1) / PCG_THREADS;
+    if (grpt <= 1) return launch_pcg_grid<T, INIT, 1>(d, sB, ncta, max_iter, tol, refuse, nrep, px, st);
+    if (grpt <= 2) return launch_pcg_grid<T, INIT, 2>(d, sB, ncta, max_iter, tol, refuse, nrep, px, st);
+    if (grpt <= 4) return launch_pcg_grid<T, INIT, 4>(d, sB, ncta, max_iter, tol, refuse, nrep, px, st);
+  }
   if (rpt <= 4) return launch_pcg_reg<T, INIT, 4>(d, sB, cl, max_iter, tol, refuse, nrep, px, st);
   if (rpt <= 8) return launch_pcg_reg<T, INIT, 8>(d, sB, cl, max_iter, tol, refuse, nrep, px, st);
   if (px.ws > 1) return cudaErrorNotSupported;  // callers fall back to fold + NCCL before reaching this
@@ -1244,7 +1315,9 @@ template <typename T>
 bool pcg_reg_kernel_available(const Dev<T> &d) {
   const int cl = pcg_cluster_size();
   const int rows = 9 * ((d.nC + cl - 1) / cl);
-  return (rows + PCG_THREADS - 1) / PCG_THREADS <= 8;
+  if ((rows + PCG_THREADS - 1) / PCG_THREADS <= 2) return true;
+  const int ncta = pcg_grid_ctas(d.nC);
+  return (9 * ((d.nC + ncta - 1) / ncta) + PCG_THREADS - 1) / PCG_THREADS <= 4;
 }
 
 template <typename T>

@@ -320,3 +320,24 @@ def test_full_size_venice_properties_and_parity():
     dx0, it0, _, _ = O.schur_pcg(HppD, HllD, W, None, g, np.zeros(9 * P.nC + 3 * P.nP), 8, 0.0, 1e300)
     assert it == it0 == 8
     assert rel_fro(S.read(capi.BUF_DX), dx0) <= 1e-8
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_many_cameras_cooperative_grid_pcg_kernel(dtype):
+    """3000 cameras do not fit one 16-CTA cluster at <= 2 rows per thread: the camera-space PCG kernel runs as a
+    cooperative grid (global partials + grid barrier) instead.  Same checks as for the cluster flavour."""
+    P = make_synthetic(3000, 40000, 300000, seed=17)  # >= 13 observations per camera: every Hpp block is well posed
+    S, O = _pair(P, dtype)
+    S.linearize()
+    region = 1e3
+    S.process_diag(region)
+    r, J, Hpp, Hll, W, g, HppD, HllD = _oracle_system(O, P, region)
+    it, done = S.solve(max_iter=10, tol=0.0, refuse_ratio=1e300)
+    dx0, it0, done0, _ = O.schur_pcg(HppD, HllD, W, None, g, np.zeros(9 * P.nC + 3 * P.nP), 10, 0.0, 1e300)
+    assert (it, done) == (it0, done0)
+    assert rel_fro(S.read(capi.BUF_DX), dx0) <= TOL[np.dtype(dtype)]["dx"]
+    it, done = S.solve(max_iter=100, tol=1e-1, refuse_ratio=1.0)   # warm start + reference stopping rules
+    dx1, it1, done1, _ = O.schur_pcg(HppD, HllD, W, None, g, dx0, 100, 1e-1, 1.0)
+    if dtype == np.float64:
+        assert (it, done) == (it1, done1)
+    assert rel_fro(S.read(capi.BUF_DX), dx1) <= 10 * TOL[np.dtype(dtype)]["dx"]
