@@ -447,7 +447,7 @@ __host__ __device__ constexpr size_t schur_smem_bytes() {
 }
 
 template <typename T, bool IMPLICIT, int MODE, int VAR>
-__global__ void __launch_bounds__(TE, 3) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
+__global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
   constexpr int K = IMPLICIT ? 24 : 27;
   constexpr bool VEC = (VAR & 1) != 0, LDCS = (VAR & 2) != 0, PREF = (VAR & 4) != 0;
   if (check_active && !d.st->active) return;

@@ -92,3 +92,33 @@ def test_two_gpus_match_single_rank_oracle(tmp_path, implicit):
     x_gpu = np.concatenate([r0["cam"].ravel(), r0["pt"].ravel()])
     assert rel_fro(x_gpu, x1) <= 1e-7
     assert np.array_equal(r0["pt"], r1["pt"])                       # get_params gathers the full point array on every rank
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+@pytest.mark.timeout(600)
+def test_facade_world_size_two_threads_in_one_process(tmp_path):
+    """The C++ facade drives deviceUsed = {0, 1} from two host threads of ONE process (like the reference's single
+    process): NCCL ranks + the peer exchange through plain peer access instead of CUDA IPC."""
+    import re
+    import subprocess
+    from conftest import ROOT
+    from megba_b200.synthetic import make_synthetic, read_bal, write_bal
+    env = dict(os.environ)
+    env.pop("CC", None)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-s"], check=True, env=env)
+    P = make_synthetic(20, 900, 4000, seed=13)
+    path = str(tmp_path / "problem-20-900-pre.txt")
+    write_bal(path, P)
+    r = subprocess.run([os.path.join(ROOT, "build", "examples", "BAL_Double_analytical"), "--path", path, "--world_size", "2",
+                        "--max_iter", "4", "--solver_max_iter", "40", "--solver_tol", "1e-6", "--tau", "1e4",
+                        "--epsilon1", "1e-3", "--epsilon2", "1e-12"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"RESULT iterations (\d+) final_cost (\S+) camera_sum (\S+)", r.stdout)
+    assert m, r.stdout
+    Q = read_bal(path)
+    O = Oracle(Q.nC, Q.nP, Q.cam_idx, Q.pt_idx, Q.obs)
+    x, k, tr = O.lm_solve(Q.x(), lm_max_iter=4, initial_region=1e4, eps1=1e-3, eps2=1e-12, pcg_max_iter=40, pcg_tol=1e-6,
+                          pcg_refuse=1.0)
+    assert int(m.group(1)) == len(tr) - 1
+    assert abs(float(m.group(2)) - tr[-1]["cost"]) <= 1e-8 * tr[-1]["cost"]
+    assert abs(float(m.group(3)) - x[:9 * Q.nC].sum()) <= 1e-7 * abs(x[:9 * Q.nC].sum())
