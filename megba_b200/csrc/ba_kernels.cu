@@ -450,7 +450,9 @@ template <typename T, bool IMPLICIT, int MODE, int VAR>
 __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
   constexpr int K = IMPLICIT ? 24 : 27;
   constexpr bool VEC = (VAR & 1) != 0, LDCS = (VAR & 2) != 0, PREF = (VAR & 4) != 0;
-  if (check_active && !d.st->active) return;
+  // Programmatic dependent launch: let the next kernel of the stream (the camera-space PCG kernel) be scheduled as
+  // soon as every CTA of this grid has started; it waits for our completion itself before it reads our sums.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sh_t = reinterpret_cast<T *>(smem_raw);  // [3][TE]
   T *sh_u = sh_t + 3 * TE;                    // [3][TE]
@@ -462,10 +464,19 @@ __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T
   const int slot0 = td.x, ne = td.y, pt0 = td.z, np = td.w;
   const int tid = threadIdx.x;
   T *dst = MODE != SM_BACKSUB ? sout + (size_t)(blockIdx.x % NREP) * (9 * (size_t)d.nC) : nullptr;
-  if (MODE == SM_FULL && zero_set) {  // clear the replica set the NEXT edge pass will accumulate into
-    const size_t tot = (size_t)NREP * 9 * d.nC;
-    for (size_t i = (size_t)blockIdx.x * TE + tid; i < tot; i += (size_t)gridDim.x * TE) zero_set[i] = T(0);
-  }
+  // Everything up to `dependent_ready` touches only data that is constant during a solve (tile descriptors, W/J,
+  // Hll^-1, w): when this grid was launched programmatically it overlaps the tail of the preceding camera kernel.
+  auto dependent_ready = [&]() -> bool {
+    if (check_active) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // the preceding kernel (p, state, replica sets) is complete
+      if (!d.st->active) return false;
+    }
+    if (MODE == SM_FULL && zero_set) {  // clear the replica set the NEXT edge pass will accumulate into
+      const size_t tot = (size_t)NREP * 9 * d.nC;
+      for (size_t i = (size_t)blockIdx.x * TE + tid; i < tot; i += (size_t)gridDim.x * TE) zero_set[i] = T(0);
+    }
+    return true;
+  };
   if (ne <= TE) {
     const bool valid = tid < ne;
     if (PREF) {
@@ -494,6 +505,7 @@ __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T
 #pragma unroll
       for (int k = 0; k < K; ++k) wj[k] = LDCS ? __ldcs(src + (size_t)k * TE) : __ldg(src + (size_t)k * TE);
     }
+    if (!dependent_ready()) return;
     if (MODE != SM_MAKEV) {
       T t[3];
       if (valid) {
@@ -541,6 +553,7 @@ __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T
     }
   } else {
     // a single point with more than TE observations: two passes over its slabs (rare; simple path)
+    if (!dependent_ready()) return;
     T u[3];
     if (MODE != SM_MAKEV) {
       T t[3] = {T(0), T(0), T(0)};
@@ -780,14 +793,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ double red_warp[32];
   __shared__ double slots[2];
-  PcgState st;
-  if (INIT) {
-    st.rho = 0.; st.rho_prev = 0.; st.rho_min = INFINITY; st.alpha = 0.; st.pq = 0.;
-    st.tol = tol; st.refuse = refuse; st.n = 0; st.max_iter = max_iter; st.active = 1; st.done = 0; st.refused = 0;
-  } else {
-    st = *d.st;
-    if (!st.active) return;
-  }
+  // the next edge pass may be scheduled now; it waits for our completion before it reads p / the state
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int ncta = cl.num_blocks(), rank = cl.block_rank();
   const int per = (d.nC + ncta - 1) / ncta;
   const int c0 = min(d.nC, rank * per), c1 = min(d.nC, c0 + per);
@@ -798,11 +805,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
   T *r_s = p_s + RPT * PCG_THREADS;
   T *hi_s = r_s + RPT * PCG_THREADS;  // [RPT*PCG_THREADS][9], only when !PRE_INV
   T hd[RPT][9], hi[PRE_INV ? RPT : 1][9], pj[RPT], rj[RPT], xj[RPT], xb[RPT], sj[RPT], qj[RPT], zj[RPT];
-  // ---- one wave of independent loads
+  // ---- loads that do not depend on the preceding edge pass: the rows of the damped Hpp and of its inverse
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     const int l = tid + j * PCG_THREADS;
-    pj[j] = rj[j] = xj[j] = xb[j] = sj[j] = qj[j] = zj[j] = T(0);
     if (l < nrows) {
       const int i = i0 + l, c = i / 9, k = i - 9 * c;
 #pragma unroll
@@ -814,6 +820,24 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
 #pragma unroll
         for (int m = 0; m < 9; ++m) cp_async<sizeof(T)>(hi_s + 9 * (size_t)l + m, d.HppInv + 81 * (size_t)c + 9 * k + m);
       }
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the edge pass (replica sums) and the previous state are complete
+  PcgState st;
+  if (INIT) {
+    st.rho = 0.; st.rho_prev = 0.; st.rho_min = INFINITY; st.alpha = 0.; st.pq = 0.;
+    st.tol = tol; st.refuse = refuse; st.n = 0; st.max_iter = max_iter; st.active = 1; st.done = 0; st.refused = 0;
+  } else {
+    st = *d.st;
+    if (!st.active) return;
+  }
+  // ---- the wave of loads that depend on it
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int l = tid + j * PCG_THREADS;
+    pj[j] = rj[j] = xj[j] = xb[j] = sj[j] = qj[j] = zj[j] = T(0);
+    if (l < nrows) {
+      const int i = i0 + l;
       xj[j] = d.dxc[i];
       // all replica loads are issued before the first add (a rolled loop would serialise 16 L2 round trips)
       T sbv[NREP];
@@ -1145,6 +1169,12 @@ cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st) {
 }
 int launches_of_prep() { return 2; }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("BA_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 int schur_variant() {
   static int v = -1;
   if (v < 0) {
@@ -1163,7 +1193,21 @@ static void launch_schur_edge_v(const Dev<T> &d, const T *xin, T *sout, T *zero_
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prepared = true;
   }
-  kern<<<d.nT, TE, smem, st>>>(d, xin, sout, zero_set, check_active);
+  if (check_active && pdl_enabled()) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(d.nT);
+    cfg.blockDim = dim3(TE);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, d, xin, sout, zero_set, check_active);
+  } else {
+    kern<<<d.nT, TE, smem, st>>>(d, xin, sout, zero_set, check_active);
+  }
 }
 
 template <typename T, bool IMPLICIT, int MODE>
@@ -1202,13 +1246,15 @@ static cudaError_t launch_cluster(K kernel, int cl, size_t smem, const Dev<T> &d
   cfg.blockDim = dim3(PCG_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // may be scheduled during the edge pass's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, d, sB, max_iter, tol, refuse, nrep, extra...);
 }
 
