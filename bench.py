@@ -210,7 +210,16 @@ def run_reference(args, P, dtype):
         "cpu_baseline": {"value": value, "unit": "LM it/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "LM it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "MegBA has no CPU execution path (every Device::CPU branch throws); this arm is the oracle port of its "
+                "algorithm on the host cores.  reference_gpu_solver below is MegBA's OWN CUDA code (oracle/shim build) on GPU 0.",
     }
+    if dtype == np.float64 and not args.implicit and not args.no_cpu_baseline:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                line["reference_gpu_solver"] = reference_gpu_solver(P, args_pcg_iters=args.pcg_iters)
+        except Exception as exc:  # optional extra
+            line["reference_gpu_solver"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
 
 
