@@ -13,12 +13,17 @@
 //   k_schur_edge   <- the two cusparseSpMV calls + oursGgemvBatched(Hll^-1) of one
 //       operator application (schur_pcg_solver.cu:315-357), MakeV (:430-510) and
 //       SolveW (:513-596); implicit operators implicitETMulx / implicitEMulx
-//       (src/solver/implicit_schur_pcg_solver.cu:21-90).  W (or J) is read ONCE.
-//   k_pcg_cam   <- all camera-space vector work of a PCG iteration
-//       (schur_pcg_solver.cu:265-313,359-406): one 8-CTA cluster, DSMEM reductions,
-//       scalars stay on the device (the reference syncs the host twice per iteration).
+//       (src/solver/implicit_schur_pcg_solver.cu:21-90).  W (or J) is read ONCE per pass;
+//       modes FULL (S*p), INIT (MakeV fused with S*x0), BACKSUB, MAKEV.
+//   k_pcg_cam_reg   <- all camera-space vector work of a PCG iteration
+//       (schur_pcg_solver.cu:265-313,359-406): one 16-CTA cluster (DSMEM reductions) or, for
+//       large camera counts, a cooperative grid; rows stay in registers; scalars stay on
+//       the device (the reference syncs the host twice per iteration); with several GPUs the
+//       allreduce of the camera vector is fused in over NVLink peer memory (no NCCL call).
+//       k_pcg_cam is the global-memory fallback for sizes neither flavour covers.
 //   k_trial   <- updateDeltaXTwoVertices + forward + JdxpF + reductions
 //       (src/edge/update.cu:14-41, src/algo/lm_algo.cu:61-126).
+// The two loop kernels chain through programmatic dependent launch (griddepcontrol).
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
