@@ -545,7 +545,7 @@ struct ImplT : Impl {
   }
 
   int process_diag(double region_, int /*recover*/) override {
-    if (!(region_ > 0)) return fail(BA_ERR_ARG, "region must be positive");
+    if (!(region_ > 0)) return fail(BA_ERR_ARG, "region must be positive (got %g)", region_);
     region = region_;
     d.damp = 1. / region_;
     return BA_OK;
@@ -999,7 +999,12 @@ int ba_lm_solve(ba_solver *s, const ba_lm_options *lm, const ba_pcg_options *pcg
       double F_chk = 0.;
       BA_TRY(m->linearize(&F_chk));                                           // :189
       if (talk) printf("Iter %d error: %g, log error: %g", k, F_new / 2, std::log10(F_new / 2));
-      region /= std::max(1. / 3., 1. - std::pow(2. * rho - 1., 3));           // :197-198
+      {
+        // :197-198.  At a converged point rho_den can round to 0 (rho = +-inf / NaN); the reference would then set
+        // region to 0 or NaN and damp with inf.  Treat a non-finite ratio as a fully successful step instead.
+        const double f = std::max(1. / 3., 1. - std::pow(2. * rho - 1., 3));
+        region /= std::isfinite(f) && f > 0. ? f : 1. / 3.;
+      }
       v = 2.;
       recover = false;
       double ginf = 0.;
