@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -296,7 +296,6 @@ def run_ours(args, P, dtype):
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     st = S.stats()
     S.set_timing(False)
     n_iter = len(trace) - 1
@@ -339,6 +338,7 @@ def run_ours(args, P, dtype):
         cost = e2e_step()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None  # sampled through both timed regions (resident + end-to-end)
     itemsize = np.dtype(dtype).itemsize
     bytes_x = (9 * P.nC + 3 * P.nP) * itemsize
     e2e = {"value": args.steps / e2e_s, "unit": "LM it/s", "h2d_bytes_per_step": bytes_x,

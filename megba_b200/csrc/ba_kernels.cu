@@ -448,7 +448,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   4 = the tile's Hll^-1 blocks / w vectors are prefetched into shared memory with cp.async at kernel start
 template <typename T, int MODE, int VAR>
 __host__ __device__ constexpr size_t schur_smem_bytes() {
-  return sizeof(T) * (6 * TE + 9 * TE + ((VAR & 4) ? 12 * TE : 0)) + sizeof(int) * TE;
+  // t (3), u (3), staging / Hll^-1 prefetch (9) scalars per slot, the w prefetch (3) only in the modes that read w.
+  // Keeping this small matters: what is not carved out as shared memory is L1, which the p gather lives in
+  // (edge pass 272 -> 257 us when the prefetch buffer stopped having storage of its own).
+  return sizeof(T) * (6 * TE + 9 * TE + (((VAR & 4) && MODE != SM_FULL) ? 3 * TE : 0)) + sizeof(int) * TE;
 }
 
 template <typename T, bool IMPLICIT, int MODE, int VAR>
@@ -461,10 +464,10 @@ __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sh_t = reinterpret_cast<T *>(smem_raw);  // [3][TE]
   T *sh_u = sh_t + 3 * TE;                    // [3][TE]
-  T *sv = sh_u + 3 * TE;                      // [TE*9] gather / scatter staging
-  T *hv = sv + 9 * TE;                        // [TE*9] prefetched Hll^-1 (PREF only)
-  T *hw = hv + (PREF ? 9 * TE : 0);           // [TE*3] prefetched w      (PREF only)
-  int *sc = reinterpret_cast<int *>(hw + (PREF ? 3 * TE : 0));
+  T *sv = sh_u + 3 * TE;                      // [TE*9] scatter staging (second half of the kernel)
+  T *hv = sv;                                 // [TE*9] prefetched Hll^-1 (first half): same storage, a barrier apart
+  T *hw = sv + 9 * TE;                        // [TE*3] prefetched w      (PREF, modes that read w)
+  int *sc = reinterpret_cast<int *>(hw + ((PREF && MODE != SM_FULL) ? 3 * TE : 0));
   const int4 td = d.tile[blockIdx.x];
   const int slot0 = td.x, ne = td.y, pt0 = td.z, np = td.w;
   const int tid = threadIdx.x;
