@@ -1183,6 +1183,14 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+// Function attributes (dynamic shared memory size, non-portable cluster size) are per DEVICE; one process may drive
+// several GPUs from several host threads, so the "already set" flags are kept per device ordinal.
+static bool *device_flag(bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &flags[dev & 63];
+}
+
 int schur_variant() {
   static int v = -1;
   if (v < 0) {
@@ -1196,10 +1204,11 @@ template <typename T, bool IMPLICIT, int MODE, int VAR>
 static void launch_schur_edge_v(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
   auto kern = k_schur_edge<T, IMPLICIT, MODE, VAR>;
   constexpr size_t smem = schur_smem_bytes<T, MODE, VAR>();
-  static bool prepared = false;
-  if (!prepared) {
+  static bool prepared_dev[64] = {};
+  bool *prepared = device_flag(prepared_dev);
+  if (!*prepared) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prepared = true;
+    *prepared = true;
   }
   if (check_active && pdl_enabled()) {
     cudaLaunchConfig_t cfg = {};
@@ -1272,11 +1281,12 @@ static cudaError_t launch_pcg_reg(const Dev<T> &d, T *sB, int cl, int max_iter, 
   constexpr bool PRE = RPT <= 1 || sizeof(T) == 4;
   auto kern = k_pcg_cam_reg<T, INIT, RPT, PRE, false>;
   const size_t smem = (2 + (PRE ? 0 : 9)) * (size_t)RPT * PCG_THREADS * sizeof(T);
-  static bool prepared = false;  // per instantiation
-  if (!prepared) {
+  static bool prepared_dev[64] = {};  // per instantiation and device
+  bool *prepared = device_flag(prepared_dev);
+  if (!*prepared) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prepared = true;
+    *prepared = true;
   }
   return launch_cluster(kern, cl, smem, d, (const T *)sB, max_iter, tol, refuse, nrep, st, px);
 }
@@ -1320,10 +1330,11 @@ static cudaError_t launch_pcg_grid(const Dev<T> &d, T *sB, int ncta, int max_ite
   constexpr bool PRE = RPT <= 1;
   auto kern = k_pcg_cam_reg<T, INIT, RPT, PRE, true>;
   const size_t smem = (2 + (PRE ? 0 : 9)) * (size_t)RPT * PCG_THREADS * sizeof(T);
-  static bool prepared = false;
-  if (!prepared) {
+  static bool prepared_dev[64] = {};
+  bool *prepared = device_flag(prepared_dev);
+  if (!*prepared) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prepared = true;
+    *prepared = true;
   }
   Dev<T> dd = d;
   const T *sBc = sB;
