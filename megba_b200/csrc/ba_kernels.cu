@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, T *sB, int ma
       acc += (double)(d.p[i] * qi);
     }
     const double pq = cluster_sum(acc, red_warp, &slots[0], cl);
-    const T alpha = (T)(st.rho / pq);           // :385
+    const T alpha = pq != 0. ? (T)(st.rho / pq) : T(0);  // p.q = 0 only for a vanished search direction           // :385
     st.alpha = (double)alpha; st.pq = pq;
     for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
       const T xi = x[i];
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, T *sB, int ma
     } else {
       st.rho_min = fmin(st.rho_min, rho_new);   // :296
       if (!INIT) {
-        const T beta = (T)(rho_new / st.rho);   // :299
+        const T beta = st.rho != 0. ? (T)(rho_new / st.rho) : T(0);   // :299
         for (int i = i0 + tid; i < i1; i += PCG_THREADS) {
           const T pv = d.z[i] + beta * d.p[i];
           d.p[i] = pv;
@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
   }
   if (!INIT) {
     const double pq = cl.sum(acc, red_warp, &slots[0], d.partials);
-    const T alpha = (T)(st.rho / pq);          // :385
+    const T alpha = pq != 0. ? (T)(st.rho / pq) : T(0);  // p.q = 0 only for a vanished search direction          // :385
     st.alpha = (double)alpha; st.pq = pq;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
@@ -976,7 +976,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
       cont = false;
     } else {
       st.rho_min = fmin(st.rho_min, rho_new);  // :296
-      if (!INIT) beta = (T)(rho_new / st.rho); // :299
+      if (!INIT) beta = st.rho != 0. ? (T)(rho_new / st.rho) : T(0); // :299
       st.rho_prev = st.rho;
       st.rho = rho_new;
     }

@@ -341,3 +341,30 @@ def test_many_cameras_cooperative_grid_pcg_kernel(dtype):
     if dtype == np.float64:
         assert (it, done) == (it1, done1)
     assert rel_fro(S.read(capi.BUF_DX), dx1) <= 10 * TOL[np.dtype(dtype)]["dx"]
+
+
+def test_empty_graph_and_unobserved_vertices():
+    """No observations at all, and vertices without observations inside a normal graph: nothing crashes, the unobserved
+    blocks stay zero and the observed part matches the oracle run on the same (ragged) input."""
+    S = capi.Solver(2, 3, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 2)))
+    S.set_params(np.zeros((2, 9)), np.zeros((3, 3)))
+    assert S.linearize() == 0.0
+    it, done = S.solve(max_iter=5, tol=1e-1, refuse_ratio=1.0)
+    assert np.all(S.read(capi.BUF_DX) == 0.0)
+    # camera 5 and points 7, 8 have no observations
+    P = make_synthetic(5, 7, 30, seed=3)
+    cam = np.vstack([P.cam, P.cam[:1] + 0.1])
+    pt = np.vstack([P.pt, P.pt[:2] + 0.1])
+    S = capi.Solver(6, 9, P.cam_idx, P.pt_idx, P.obs)
+    S.set_params(cam, pt)
+    O = Oracle(6, 9, P.cam_idx, P.pt_idx, P.obs)
+    cost = S.linearize()
+    r, J = O.forward(cam, pt)
+    Hpp, Hll, W, g = O.build(r, J)
+    assert abs(cost - O.cost(r)) <= 1e-10 * O.cost(r)
+    assert rel_fro(S.read(capi.BUF_HPP), Hpp) <= 1e-10 and np.all(S.read(capi.BUF_HPP)[5] == 0)
+    assert rel_fro(S.read(capi.BUF_HLL), Hll) <= 1e-10 and np.all(S.read(capi.BUF_HLL)[7:] == 0)
+    S.process_diag(1e3)
+    it, done = S.solve(max_iter=10, tol=0.0, refuse_ratio=1e300)
+    dx = S.read(capi.BUF_DX)
+    assert np.all(np.isfinite(dx)) and np.all(dx[9 * 5:9 * 6] == 0) and np.all(dx[9 * 6 + 21:] == 0)
