@@ -899,12 +899,20 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
       const int l = tid + j * PCG_THREADS;
       if (l < nrows) {
         const int i = i0 + l;
-        T sb = T(0), sa = T(0);
-        for (int r = 0; r < px.ws; ++r) {
-          const T *peer = reinterpret_cast<const T *>(px.data[r]) + (size_t)px.parity * 2 * rs;
-          sb += __ldcv(peer + i);
-          if (INIT) sa += __ldcv(peer + rs + i);
+        // all peer loads are issued before the first add: a rolled loop would pay one NVLink round trip per rank
+        T pb[8], pa[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          pb[r] = pa[r] = T(0);
+          if (r < px.ws) {
+            const T *peer = reinterpret_cast<const T *>(px.data[r]) + (size_t)px.parity * 2 * rs;
+            pb[r] = __ldcv(peer + i);
+            if (INIT) pa[r] = __ldcv(peer + rs + i);
+          }
         }
+        T sb = T(0), sa = T(0);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { sb += pb[r]; sa += pa[r]; }  // rank order: identical on every rank
         sj[j] = sb;
         if (INIT) rj[j] = d.gc[i] - sa;
       }
