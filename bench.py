@@ -321,6 +321,16 @@ def run_ours(args, P, dtype):
                 "linearize": {"algorithmic_bytes": a_lin,
                               "avg_ms": st["linearize_ms"] / max(st["linearize_calls"], 1),
                               "achieved": a_lin / (st["linearize_ms"] / max(st["linearize_calls"], 1) * 1e-3) / 1e9}}
+    # whole LM iteration against the same roofline: linearisation + trial evaluation +
+    # (init pass + n_k PCG passes + back-substitution) x A_pcg, with the PCG iteration count actually run
+    itemsize_ = np.dtype(dtype).itemsize
+    a_eval = (P.nE * (8 + 2 * itemsize_) + P.nP * 6 * itemsize_ + P.nC * 18 * itemsize_) / ws
+    n_lin = st["linearize_calls"]
+    lm_bytes = n_lin * a_lin + args.steps * a_eval + (st["pcg_iters"] + 2 * args.steps) * a_pcg
+    roofline["lm_iteration"] = {"algorithmic_bytes_per_step": lm_bytes / args.steps,
+                                "achieved": lm_bytes / (ms_total * 1e-3) / 1e9, "unit": "GB/s",
+                                "frac": lm_bytes / (ms_total * 1e-3) / 1e9 / peak,
+                                "what": "all algorithmic bytes of the timed LM iterations / timed region (per rank)"}
     launches = st["launches"]
 
     # ---------------- end-to-end arm: K solve() calls on host buffers
