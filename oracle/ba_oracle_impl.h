@@ -330,6 +330,39 @@ void FN(orc_hpl_mul)(const orc_graph *G, const R *W, const R *J, const R *yp, R 
   }
 }
 
+/* Camera-major copies of the coupling data.  The reference keeps TWO value arrays, Hpl (camera-major rows) and Hlp
+ * (point-major rows), so that both SpMVs stream their matrix (include/linear_system/schur_linear_system.h:22-27);
+ * the oracle does the same for its timed solve: Wcm[k] / Jcm[k] is the block of edge cam_edges[k].               */
+static R *FN(camera_major_copy)(const orc_graph *G, const R *src, int width) {
+  R *dst = (R *)malloc(sizeof(R) * (size_t)width * (size_t)(G->nE ? G->nE : 1));
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < G->nE; ++k) memcpy(dst + (size_t)width * k, src + (size_t)width * G->cam_edges[k], sizeof(R) * width);
+  return dst;
+}
+
+static void FN(hpl_mul_cm)(const orc_graph *G, const R *Wcm, const R *Jcm, const R *yp, R *q) {
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t c = 0; c < G->nC; ++c) {
+    R acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t k = G->cam_ptr[c]; k < G->cam_ptr[c + 1]; ++k) {
+      const R *y = yp + 3 * (int64_t)G->pt_idx[G->cam_edges[k]];
+      if (Wcm) {
+        const R *We = Wcm + 27 * k;
+        for (int yy = 0; yy < 9; ++yy)
+          for (int i = 0; i < 3; ++i) acc[yy] += We[3 * yy + i] * y[i];
+      } else {
+        for (int row = 0; row < 2; ++row) {
+          const R *Jr = Jcm + 24 * k + 12 * row;
+          R jpx = 0;
+          for (int i = 0; i < 3; ++i) jpx += Jr[9 + i] * y[i];
+          for (int yy = 0; yy < 9; ++yy) acc[yy] += Jr[yy] * jpx;
+        }
+      }
+    }
+    for (int i = 0; i < 9; ++i) q[9 * c + i] = acc[i];
+  }
+}
+
 /* q = S p = Hpp p - Hpl Hll^-1 Hlp p  (one PCG operator application,
  * schur_pcg_solver.cu:315-366).  tmp: 3nP scratch.                              */
 void FN(orc_schur_mul)(const orc_graph *G, const R *HppD, const R *HllInv, const R *W,
@@ -344,6 +377,22 @@ void FN(orc_schur_mul)(const orc_graph *G, const R *HppD, const R *HllInv, const
       R s = 0;
       for (int j = 0; j < 9; ++j) s += HppD[81 * c + 9 * i + j] * p[9 * c + j];
       q[9 * c + i] = s - q[9 * c + i]; /* oursGgemvBatched<T,1,-1> :363-365 */
+    }
+}
+
+/* same operator as orc_schur_mul, with the Hpl product streaming the camera-major copy */
+static void FN(schur_mul_cm)(const orc_graph *G, const R *HppD, const R *HllInv, const R *W, const R *J, const R *Wcm,
+                             const R *Jcm, const R *p, R *tmp, R *q) {
+  const int64_t nC = G->nC, nP = G->nP;
+  FN(orc_hlp_mul)(G, W, J, p, tmp);
+  FN(block_gemv)(nP, 3, HllInv, tmp, tmp);
+  FN(hpl_mul_cm)(G, Wcm, Jcm, tmp, q);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nC; ++c)
+    for (int i = 0; i < 9; ++i) {
+      R s = 0;
+      for (int j = 0; j < 9; ++j) s += HppD[81 * c + 9 * i + j] * p[9 * c + j];
+      q[9 * c + i] = s - q[9 * c + i];
     }
 }
 
@@ -377,14 +426,16 @@ int FN(orc_schur_pcg)(const orc_graph *G, const R *HppD, const R *HllD, const R 
   R *pN = (R *)malloc(sizeof(R) * nc9);
   R *ax = (R *)malloc(sizeof(R) * nc9);
   R *xbk = (R *)malloc(sizeof(R) * nc9);
+  R *Wcm = W ? FN(camera_major_copy)(G, W, 27) : NULL;
+  R *Jcm = W ? NULL : FN(camera_major_copy)(G, J, 24);
   FN(orc_block_inverse)(nP, 3, HllD, HllInv);
   /* MakeV: w = Hll^-1 g_l ; v = g_c - Hpl w   (:467-493, beta = 1/worldSize = 1) */
   FN(block_gemv)(nP, 3, HllInv, g + nc9, w);
-  FN(orc_hpl_mul)(G, W, J, w, v);
+  FN(hpl_mul_cm)(G, Wcm, Jcm, w, v);
   for (int64_t i = 0; i < nc9; ++i) v[i] = g[i] - v[i];
   /* PCG */
   FN(orc_block_inverse)(nC, 9, HppD, HppInv); /* :199 */
-  FN(orc_schur_mul)(G, HppD, HllInv, W, J, dx, tmp, ax); /* :202-251 with x0 */
+  FN(schur_mul_cm)(G, HppD, HllInv, W, J, Wcm, Jcm, dx, tmp, ax); /* :202-251 with x0 */
   for (int64_t i = 0; i < nc9; ++i) rN[i] = v[i] - ax[i]; /* :182,256 */
   int n = 0, done = 0;
   R rhoN = 0, rhoNm1 = 0;
@@ -404,7 +455,7 @@ int FN(orc_schur_pcg)(const orc_graph *G, const R *HppD, const R *HllD, const R 
     } else {
       memcpy(pN, ax, sizeof(R) * nc9);         /* :310 */
     }
-    FN(orc_schur_mul)(G, HppD, HllInv, W, J, pN, tmp, ax); /* q :315-366 */
+    FN(schur_mul_cm)(G, HppD, HllInv, W, J, Wcm, Jcm, pN, tmp, ax); /* q :315-366 */
     const double dot_sum = FN(dotd)(nc9, pN, ax);          /* :368-384 */
     const R alpha = (R)(rhoN / dot_sum);                   /* :385 */
     memcpy(xbk, dx, sizeof(R) * nc9);                      /* :389 */
@@ -423,7 +474,7 @@ int FN(orc_schur_pcg)(const orc_graph *G, const R *HppD, const R *HllD, const R 
   if (iters_out) *iters_out = n;
   if (rho_out) *rho_out = (double)rhoN;
   free(HllInv); free(HppInv); free(w); free(tmp); free(v);
-  free(rN); free(pN); free(ax); free(xbk);
+  free(rN); free(pN); free(ax); free(xbk); free(Wcm); free(Jcm);
   return done;
 }
 
