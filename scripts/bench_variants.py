@@ -13,6 +13,10 @@ def child():
     import numpy as np
     from megba_b200 import capi
     from megba_b200.synthetic import BAProblem
+    if os.environ.get("BA_LIB"):  # an experimental build of the same library (e.g. build/exp/libmegba_b200_g32.so)
+        capi.LIB_PATH = os.path.join(ROOT, os.environ["BA_LIB"])
+    if os.environ.get("BA_LIB"):  # an experimental build of the same library (e.g. build/exp/libmegba_b200_g32.so)
+        capi.LIB_PATH = os.path.join(ROOT, os.environ["BA_LIB"])
     z = np.load(CACHE)
     P = BAProblem(int(z["nC"]), int(z["nP"]), int(z["nE"]), z["cam_idx"], z["pt_idx"], z["obs"], z["cam"], z["pt"])
     dtype = np.float64 if os.environ.get("BA_DTYPE", "f64") == "f64" else np.float32
@@ -28,9 +32,10 @@ def child():
     st = S.stats()
     a_pcg, _ = S.algorithmic_bytes()
     k = st["schur_apply_ms"] / st["schur_apply_timed"]
-    print(f"VAR={os.environ.get('BA_VAR','-')} edge {k*1e3:8.1f} us  {a_pcg/k/1e6:7.0f} GB/s   pcg loop "
+    print(f"VAR={os.environ.get('BA_VAR','-')} LIB={os.environ.get('BA_LIB','default')} edge {k*1e3:8.1f} us  {a_pcg/k/1e6:7.0f} GB/s   pcg loop "
           f"{st['pcg_loop_ms']/st['pcg_iters']*1e3:7.1f} us/iter   cam kernel {st['pcg_cam_ms']/max(st['pcg_cam_timed'],1)*1e3:6.1f} us   "
           f"solve {st['solve_ms']/3:7.2f} ms", flush=True)
+    print(f"        check: |dx|, |x| = {S.step_norms()}", flush=True)  # must agree between variants to ~1e-12 relative
     # same three solves without per-launch events: host wall clock around the (synchronous) call
     import time
     S.set_timing(False)
