@@ -76,7 +76,7 @@ static int partition_points(int64_t nP, const int64_t *deg, int ws, int64_t *cut
 static int build_host_graph(const ba_options &opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx,
                             const int32_t *pt_idx, HostGraph &g, std::string &err) {
   g.nC = nC; g.nP = nP; g.nE = nE;
-  if (nC <= 0 || nP <= 0 || nE < 0 || nC > (1 << 28) || nP > (1ll << 30)) { err = "bad problem size"; return BA_ERR_ARG; }
+  if (nC <= 0 || nP <= 0 || nE < 0 || nC >= (1 << 24) || nP > (1ll << 30)) { err = "bad problem size"; return BA_ERR_ARG; }
   std::vector<int64_t> deg(nP, 0);
   for (int64_t e = 0; e < nE; ++e) {
     if (cam_idx[e] < 0 || cam_idx[e] >= nC || pt_idx[e] < 0 || pt_idx[e] >= nP) { err = "vertex index out of range"; return BA_ERR_ARG; }
@@ -120,7 +120,11 @@ static int build_host_graph(const ba_options &opt, int64_t nC, int64_t nP, int64
       close_tile();
       g.pt_slot[p] = slab * TE;
       g.tile.push_back(make_int4(slab * TE, (int)dg, p, 1));
-      slab += (int)((dg + TE - 1) / TE);
+      // the point's further slabs get empty tiles: tile index == slab index is what lets the edge kernels address a
+      // CTA's slots from blockIdx alone, before the descriptor has been read
+      const int nslab = (int)((dg + TE - 1) / TE);
+      for (int k = 1; k < nslab; ++k) g.tile.push_back(make_int4((slab + k) * TE, 0, p, 0));
+      slab += nslab;
       continue;
     }
     if (cur_np > 0 && (cur_ne + dg > TE || cur_np == TE)) close_tile();
@@ -195,7 +199,7 @@ struct Impl {
   bool timing = false;
   int timing_stride = 1;  // per-launch events are recorded for every timing_stride-th PCG iteration
   ba_stats stats{};
-  bool linearized = false, have_step = false;
+  bool linearized = false;
   double region = 1e3;
   virtual ~Impl() {}
   int fail(int code, const char *fmt, ...) {
@@ -469,7 +473,6 @@ struct ImplT : Impl {
     }
     BA_CUDA(cudaStreamSynchronize(stream));
     linearized = false;
-    have_step = false;
     return BA_OK;
   }
 
@@ -599,7 +602,7 @@ struct ImplT : Impl {
     // The loop is enqueued in chunks; the device-side `active` flag turns the remaining launches of a
     // chunk into no-ops once the reference's do-while would have exited.  The state of chunk k is polled
     // only after chunk k+1 has been enqueued, so the GPU never waits for the host.
-    int launched = 0, n_seen = 0, chunk_id = 0;
+    int launched = 0, chunk_id = 0;
     struct Pending { int slot; bool valid; } pend{0, false};
     std::vector<std::pair<size_t, int>> loc_schur, loc_cam;  // (event pair, iteration) of the sampled launches
     bool finished = false;
@@ -607,7 +610,6 @@ struct ImplT : Impl {
       BA_CUDA(cudaEventSynchronize(st_event[pd.slot]));
       const PcgState &hs = h_st[pd.slot];
       if (!hs.active) finished = true;
-      n_seen = hs.n;
       return BA_OK;
     };
     while (launched < o->max_iter && !finished) {
@@ -662,7 +664,6 @@ struct ImplT : Impl {
     stats.pcg_iters += h_st[0].n;
     if (iters) *iters = h_st[0].n;
     if (done) *done = h_st[0].done;
-    have_step = true;
     return BA_OK;
   }
 

@@ -35,6 +35,12 @@ namespace cg = cooperative_groups;
 
 namespace ba {
 
+#ifndef BA_EARLY
+#define BA_EARLY 1  // edge pass: slot streams requested before the tile descriptor has arrived
+#endif
+#ifndef BA_TPP
+#define BA_TPP 1    // edge pass: up to 4 threads per point in the point phase
+#endif
 #ifndef BA_DEFAULT_VAR
 #define BA_DEFAULT_VAR 5
 #endif
@@ -458,6 +464,10 @@ template <typename T, bool IMPLICIT, int MODE, int VAR>
 __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
   constexpr int K = IMPLICIT ? 24 : 27;
   constexpr bool VEC = (VAR & 1) != 0, LDCS = (VAR & 2) != 0, PREF = (VAR & 4) != 0;
+  // Requesting the slot streams before the tile descriptor has arrived pays for the fp32 and the matrix-free kernels
+  // (-3 %); the fp64 explicit kernel measured 257 us early / 256 us late with the 4-thread point phase off / on, but
+  // 277 us with both (profiles/r01_edge_variants_early_tpp.txt), so it keeps the late order.
+  constexpr bool EARLY = BA_EARLY && (sizeof(T) == 4 || IMPLICIT);
   // Programmatic dependent launch: let the next kernel of the stream (the camera-space PCG kernel) be scheduled as
   // soon as every CTA of this grid has started; it waits for our completion itself before it reads our sums.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -468,9 +478,24 @@ __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T
   T *hv = sv;                                 // [TE*9] prefetched Hll^-1 (first half): same storage, a barrier apart
   T *hw = sv + 9 * TE;                        // [TE*3] prefetched w      (PREF, modes that read w)
   int *sc = reinterpret_cast<int *>(hw + ((PREF && MODE != SM_FULL) ? 3 * TE : 0));
-  const int4 td = d.tile[blockIdx.x];
-  const int slot0 = td.x, ne = td.y, pt0 = td.z, np = td.w;
   const int tid = threadIdx.x;
+  // Tile index == slab index (the graph builder pads a point that spans several slabs with empty tiles), so this
+  // thread's slot is known before the tile descriptor arrives: the descriptor, the slot's camera / point indices and
+  // its W (or J) block are requested together instead of in three dependent round trips.  Slots past `ne` are padding
+  // (zero blocks, camera 0): loading them is harmless and they take no part in the sums.
+  const int4 td = __ldg(d.tile + blockIdx.x);
+  const int slot_mine = (int)blockIdx.x * TE + tid;
+  // camera (< 2^24, checked by ba_create) and local point index (< TE = 2^8) share one register until they are used
+  int c_lp = 0;
+  T wj[K];
+  auto load_slot = [&]() {
+    c_lp = __ldg(d.e_cam + slot_mine) | ((int)__ldg(d.e_lp + slot_mine) << 24);
+    const T *src = d.WJ + (size_t)blockIdx.x * (K * TE) + tid;
+#pragma unroll
+    for (int k = 0; k < K; ++k) wj[k] = LDCS ? __ldcs(src + (size_t)k * TE) : __ldg(src + (size_t)k * TE);
+  };
+  if (EARLY) load_slot();
+  const int slot0 = td.x, ne = td.y, pt0 = td.z, np = td.w;
   T *dst = MODE != SM_BACKSUB ? sout + (size_t)(blockIdx.x % NREP) * (9 * (size_t)d.nC) : nullptr;
   // Everything up to `dependent_ready` touches only data that is constant during a solve (tile descriptors, W/J,
   // Hll^-1, w): when this grid was launched programmatically it overlaps the tail of the preceding camera kernel.
@@ -480,8 +505,8 @@ __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T
       if (!d.st->active) return false;
     }
     if (MODE == SM_FULL && zero_set) {  // clear the replica set the NEXT edge pass will accumulate into
-      const size_t tot = (size_t)NREP * 9 * d.nC;
-      for (size_t i = (size_t)blockIdx.x * TE + tid; i < tot; i += (size_t)gridDim.x * TE) zero_set[i] = T(0);
+      const unsigned tot = (unsigned)NREP * 9u * (unsigned)d.nC;  // nC < 2^24 (ba_create): fits 32 bits
+      for (unsigned i = blockIdx.x * TE + tid; i < tot; i += gridDim.x * TE) zero_set[i] = T(0);
     }
     return true;
   };
@@ -498,66 +523,68 @@ __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T
       }
       cp_async_commit();
     }
-    int s0 = 0, s1 = 0;
-    if (MODE != SM_MAKEV && tid < np) {
-      s0 = d.pt_slot[pt0 + tid] - slot0;
-      s1 = (tid + 1 < np) ? d.pt_slot[pt0 + tid + 1] - slot0 : ne;
+    // point phase: 4 / 2 / 1 threads per point, so that the whole CTA is not parked at a barrier behind np <= TE/4
+    // threads that walk their observation lists alone
+    const int tsh = !BA_TPP ? 0 : np <= TE / 4 ? 2 : np <= TE / 2 ? 1 : 0;
+    const int tpp = 1 << tsh, pi = tid >> tsh, sub = tid & (tpp - 1);
+    const bool pact = pi < np;
+    int s01 = 0;  // first slot | (end slot << 16) of this thread's point, relative to the tile (both <= TE)
+    if (MODE != SM_MAKEV && pact) {
+      const int s0 = __ldg(d.pt_slot + pt0 + pi) - slot0;
+      const int s1 = (pi + 1 < np) ? __ldg(d.pt_slot + pt0 + pi + 1) - slot0 : ne;
+      s01 = s0 | (s1 << 16);
     }
-    T wj[K];
-    int c = 0, lp = 0;
-    if (valid) {
-      const int slot = slot0 + tid;
-      c = d.e_cam[slot];
-      lp = d.e_lp[slot];
-      const T *src = d.WJ + wj_base<T>(slot, K);
-#pragma unroll
-      for (int k = 0; k < K; ++k) wj[k] = LDCS ? __ldcs(src + (size_t)k * TE) : __ldg(src + (size_t)k * TE);
-    }
+    if (!EARLY && valid) load_slot();
     if (!dependent_ready()) return;
     if (MODE != SM_MAKEV) {
       T t[3];
       if (valid) {
         __align__(16) T x[CamPad<T>::N];
-        gather_cam<T, VEC>(xin, c, x);
+        gather_cam<T, VEC>(xin, c_lp & 0xffffff, x);
         edge_t<T, IMPLICIT>(wj, x, t);
       }
       if (valid) { sh_t[tid] = t[0]; sh_t[TE + tid] = t[1]; sh_t[2 * TE + tid] = t[2]; }
     }
     if (PREF) cp_async_wait_all();
     if (MODE != SM_MAKEV || PREF) __syncthreads();
-    if (tid < np) {
-      const int p = pt0 + tid;
-      T u[3];
+    {
+      const int p = pt0 + pi;
       if (MODE != SM_MAKEV) {
         T t0 = T(0), t1 = T(0), t2 = T(0);
-        for (int s = s0; s < s1; ++s) { t0 += sh_t[s]; t1 += sh_t[TE + s]; t2 += sh_t[2 * TE + s]; }
-        T hi[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) hi[k] = PREF ? hv[9 * tid + k] : __ldg(d.HllInv + 9 * (size_t)p + k);
-#pragma unroll
-        for (int y = 0; y < 3; ++y) u[y] = hi[3 * y] * t0 + hi[3 * y + 1] * t1 + hi[3 * y + 2] * t2;
-        if (MODE == SM_INIT) {  // u = Hll^-1 Hlp x0 - w: one pass yields  Hpl Hll^-1 Hlp x0 - Hpl w
-#pragma unroll
-          for (int y = 0; y < 3; ++y) u[y] -= PREF ? hw[3 * tid + y] : d.w[3 * (size_t)p + y];
+        if (pact)
+          for (int s = (s01 & 0xffff) + sub, s1 = s01 >> 16; s < s1; s += tpp) { t0 += sh_t[s]; t1 += sh_t[TE + s]; t2 += sh_t[2 * TE + s]; }
+        if (tsh >= 1) {  // CTA-uniform: every lane of every warp takes part in the exchange
+          t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 1); t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
         }
-        if (MODE == SM_BACKSUB) {
-#pragma unroll
-          for (int y = 0; y < 3; ++y) d.dxl[3 * (size_t)p + y] = (PREF ? hw[3 * tid + y] : d.w[3 * (size_t)p + y]) - u[y];
+        if (tsh >= 2) {
+          t0 += __shfl_xor_sync(0xffffffffu, t0, 2); t1 += __shfl_xor_sync(0xffffffffu, t1, 2); t2 += __shfl_xor_sync(0xffffffffu, t2, 2);
         }
-      } else {
-#pragma unroll
-        for (int y = 0; y < 3; ++y) u[y] = PREF ? hw[3 * tid + y] : d.w[3 * (size_t)p + y];
+        if (pact)
+          for (int y = sub; y < 3; y += tpp) {  // row y of u = Hll^-1 t
+            const T h0 = PREF ? hv[9 * pi + 3 * y] : __ldg(d.HllInv + 9 * (size_t)p + 3 * y);
+            const T h1 = PREF ? hv[9 * pi + 3 * y + 1] : __ldg(d.HllInv + 9 * (size_t)p + 3 * y + 1);
+            const T h2 = PREF ? hv[9 * pi + 3 * y + 2] : __ldg(d.HllInv + 9 * (size_t)p + 3 * y + 2);
+            T uy = h0 * t0 + h1 * t1 + h2 * t2;
+            if (MODE == SM_INIT || MODE == SM_BACKSUB) {
+              const T wy = PREF ? hw[3 * pi + y] : d.w[3 * (size_t)p + y];
+              if (MODE == SM_INIT) uy -= wy;  // u = Hll^-1 Hlp x0 - w: one pass yields  Hpl Hll^-1 Hlp x0 - Hpl w
+              else d.dxl[3 * (size_t)p + y] = wy - uy;
+            }
+            if (MODE != SM_BACKSUB) sh_u[y * TE + pi] = uy;
+          }
+      } else if (pact) {
+        for (int y = sub; y < 3; y += tpp) sh_u[y * TE + pi] = PREF ? hw[3 * pi + y] : d.w[3 * (size_t)p + y];
       }
-      if (MODE != SM_BACKSUB) { sh_u[tid] = u[0]; sh_u[TE + tid] = u[1]; sh_u[2 * TE + tid] = u[2]; }
     }
     if (MODE != SM_BACKSUB) {
       __syncthreads();
       T o[9];
       if (valid) {
+        const int lp = (unsigned)c_lp >> 24;
         const T u[3] = {sh_u[lp], sh_u[TE + lp], sh_u[2 * TE + lp]};
         edge_scatter<T, IMPLICIT>(wj, u, o);
       }
-      warp_scatter9<T>(sv, sc, o, valid ? c : -1, dst);
+      warp_scatter9<T>(sv, sc, o, valid ? (c_lp & 0xffffff) : -1, dst);
     }
   } else {
     // a single point with more than TE observations: two passes over its slabs (rare; simple path)

@@ -15,6 +15,8 @@ ap.add_argument("--pcg", type=int, default=4)
 ap.add_argument("--implicit", action="store_true")
 ap.add_argument("--dtype", default="f64")
 a = ap.parse_args()
+if os.environ.get("BA_LIB"):  # an experimental build (see scripts/bench_variants.py)
+    capi.LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.environ["BA_LIB"])
 P = make_named(a.workload)
 S = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype=np.float64 if a.dtype == "f64" else np.float32,
                 implicit=a.implicit)
