@@ -105,11 +105,11 @@ static int build_host_graph(const ba_options &opt, int64_t nC, int64_t nP, int64
   // tiles
   g.tile.clear();
   g.pt_slot.assign(g.nPl, 0);
-  int slab = 0;
+  int64_t slab = 0;  // padding can double the slot count of a pathological graph: checked against int range below
   int cur_pt0 = 0, cur_np = 0, cur_ne = 0;
   auto close_tile = [&]() {
     if (cur_np > 0) {
-      g.tile.push_back(make_int4(slab * TE, cur_ne, cur_pt0, cur_np));
+      g.tile.push_back(make_int4((int)(slab * TE), cur_ne, cur_pt0, cur_np));
       slab += 1;
     }
     cur_np = 0; cur_ne = 0;
@@ -118,24 +118,25 @@ static int build_host_graph(const ba_options &opt, int64_t nC, int64_t nP, int64
     const int64_t dg = ptr[p + 1] - ptr[p];
     if (dg > TE) {
       close_tile();
-      g.pt_slot[p] = slab * TE;
-      g.tile.push_back(make_int4(slab * TE, (int)dg, p, 1));
+      g.pt_slot[p] = (int)(slab * TE);
+      g.tile.push_back(make_int4((int)(slab * TE), (int)dg, p, 1));
       // the point's further slabs get empty tiles: tile index == slab index is what lets the edge kernels address a
       // CTA's slots from blockIdx alone, before the descriptor has been read
       const int nslab = (int)((dg + TE - 1) / TE);
-      for (int k = 1; k < nslab; ++k) g.tile.push_back(make_int4((slab + k) * TE, 0, p, 0));
+      for (int k = 1; k < nslab; ++k) g.tile.push_back(make_int4((int)((slab + k) * TE), 0, p, 0));
       slab += nslab;
       continue;
     }
     if (cur_np > 0 && (cur_ne + dg > TE || cur_np == TE)) close_tile();
     if (cur_np == 0) cur_pt0 = p;
-    g.pt_slot[p] = slab * TE + cur_ne;
+    g.pt_slot[p] = (int)(slab * TE) + cur_ne;
     cur_np += 1;
     cur_ne += (int)dg;
   }
   close_tile();
+  if ((slab + 1) * TE >= (1ll << 31)) { err = "too many observation slots on one rank"; return BA_ERR_ARG; }
   g.nT = (int)g.tile.size();
-  g.nSlabs = slab;
+  g.nSlabs = (int)slab;
   const size_t nSlots = (size_t)slab * TE;
   g.e_cam.assign(nSlots, 0);
   g.e_lp.assign(nSlots, 0);
