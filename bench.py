@@ -113,7 +113,7 @@ def oracle_lm_iteration(P, pcg_iters, implicit, dtype):
     return dt, sum(t["pcg_iters"] for t in tr), O.num_threads(), tr
 
 
-def reference_gpu_solver(P, pcg_lo=5, pcg_hi=25, args_pcg_iters=50):
+def reference_gpu_solver(P, pcg_lo=10, pcg_hi=50, args_pcg_iters=50):
     """MegBA's own SchurPCGSolver::solve (src/solver/schur_pcg_solver.cu: cuBLAS matinvBatched, cuSPARSE CSR SpMV,
     cuBLAS dot/axpy, two host syncs per iteration) compiled for sm_100a from the reference sources via oracle/shim,
     timed on this GPU on the same problem with the same damped blocks.  Two fixed iteration counts give the time per
@@ -132,7 +132,7 @@ def reference_gpu_solver(P, pcg_lo=5, pcg_hi=25, args_pcg_iters=50):
     del r, J
     ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
     out = {}
-    for n in (pcg_lo, pcg_hi, pcg_lo, pcg_hi):
+    for n in (pcg_lo, pcg_hi) * 3:
         dx = np.zeros(9 * P.nC + 3 * P.nP)
         ms = C.c_double()
         rc = L.ref_solve_timed_f64(C.c_int64(P.nC), C.c_int64(P.nP), C.c_int64(P.nE), ptr(P.cam_idx), ptr(P.pt_idx),
@@ -145,7 +145,7 @@ def reference_gpu_solver(P, pcg_lo=5, pcg_hi=25, args_pcg_iters=50):
     res = {"pcg_iters_per_sec": 1e3 / per_iter, "ms_per_pcg_iter": per_iter,
            "solve_ms": {str(k): v for k, v in out.items()},
            "what": "reference SchurPCGSolver::solve (schur_pcg_solver.cu, cuSPARSE/cuBLAS) built for sm_100a via "
-                   "oracle/shim, same GPU and problem; best of 2 per iteration count, per-iteration time by difference"}
+                   "oracle/shim, same GPU and problem; best of 3 per iteration count, per-iteration time by difference"}
     del W, Hpp, Hll, HppD, HllD
     # the reference's whole LM loop (lm_algo.cu + its kernels + its solver), same fixed-work settings as our arm
     try:
