@@ -464,10 +464,11 @@ template <typename T, bool IMPLICIT, int MODE, int VAR>
 __global__ void __launch_bounds__(TE, sizeof(T) == 4 ? 5 : 3) k_schur_edge(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
   constexpr int K = IMPLICIT ? 24 : 27;
   constexpr bool VEC = (VAR & 1) != 0, LDCS = (VAR & 2) != 0, PREF = (VAR & 4) != 0;
-  // Requesting the slot streams before the tile descriptor has arrived pays for the fp32 and the matrix-free kernels
-  // (-3 %); the fp64 explicit kernel measured 257 us early / 256 us late with the 4-thread point phase off / on, but
-  // 277 us with both (profiles/r01_edge_variants_early_tpp.txt), so it keeps the late order.
-  constexpr bool EARLY = BA_EARLY && (sizeof(T) == 4 || IMPLICIT);
+  // Requesting the slot streams before the tile descriptor has arrived pays for the fp32 kernels (-3 %); the fp64
+  // explicit kernel measured 257 us early / 256 us late with the 4-thread point phase off / on but 277 us with both,
+  // the fp64 matrix-free kernel 245 us early / 242 us late (profiles/r01_edge_variants_early_tpp.txt): fp64 keeps the
+  // late order.
+  constexpr bool EARLY = BA_EARLY && sizeof(T) == 4;
   // Programmatic dependent launch: let the next kernel of the stream (the camera-space PCG kernel) be scheduled as
   // soon as every CTA of this grid has started; it waits for our completion itself before it reads our sums.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
