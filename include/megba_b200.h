@@ -117,7 +117,9 @@ int ba_partition_points(int64_t nP, const int64_t *pt_degree, int32_t world_size
  * SchurLMLinearSystem::buildIndex/allocateResourceCUDA
  * (src/linear_system/schur_LM_linear_system.cpp:53-84, .cu:29-110).
  * cam_idx/pt_idx: vertex numbers of each observation (any order, every rank passes
- * the full list); obs[nE][2] in the solver dtype.                                  */
+ * the full list); obs[nE][2] in the solver dtype.
+ * Limits (BA_ERR_ARG otherwise): 0 < nC < 2^24, 0 < nP <= 2^30, and fewer than 2^31
+ * observation slots per rank after padding to 256-slot tiles.                      */
 int ba_create(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE,
               const int32_t *cam_idx, const int32_t *pt_idx, const void *obs,
               ba_solver **out);
