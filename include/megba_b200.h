@@ -111,6 +111,24 @@ int ba_abi_version(void);
 int ba_partition_points(int64_t nP, const int64_t *pt_degree, int32_t world_size,
                         int64_t *pt_begin);
 
+/* Host-only, no GPU needed: the observation layout ba_create builds for (opt->rank, opt->world_size) -- the
+ * counterpart of what EdgeVector::buildPositionContainer (src/edge/base_edge.cpp:224-262) and
+ * SchurLMLinearSystem::buildIndex (src/linear_system/schur_LM_linear_system.cpp:53-84) leave in the reference's
+ * CSR index arrays, exposed so that tools and the no-GPU tests can inspect it.  Every output pointer may be NULL;
+ * call once with only `sizes` to learn the array lengths.
+ *   tile[n_tiles][4]     = {first slot (== 256 * tile index), observations, first local point, points}
+ *   edge_of_slot[n_slots] = observation number stored in the slot, -1 for padding
+ *   slot_cam / slot_lp[n_slots] = camera and tile-local point index of the slot
+ *   pt_slot[n_local_points]    = first slot of each local point (its observations are contiguous, camera-ascending)
+ *   chunk[n_chunks][4]   = {camera, begin, end, 0}: ranges of the camera-major view, at most 1024 entries each
+ *   cm_slot[n_local_edges]     = slot of each camera-major entry                                              */
+typedef struct ba_layout_sizes {
+  int64_t n_tiles, n_slots, n_local_edges, n_local_points, n_chunks, pt_begin;
+} ba_layout_sizes;
+int ba_layout(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx,
+              const int32_t *pt_idx, ba_layout_sizes *sizes, int32_t *tile, int64_t *edge_of_slot,
+              int32_t *slot_cam, int32_t *slot_lp, int32_t *pt_slot, int32_t *chunk, int32_t *cm_slot);
+
 /* BaseProblem::appendVertex/appendEdge + buildIndex (src/problem/base_problem.cpp:
  * 82-125,183-214), EdgeVector::buildPositionContainer/allocateResource
  * (src/edge/base_edge.cpp:224-262, src/edge/base_edge.cu:47-103) and

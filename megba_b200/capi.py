@@ -25,7 +25,7 @@ SYMBOLS = [
     "ba_linearize", "ba_process_diag", "ba_solve", "ba_step_norms", "ba_eval_trial",
     "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
     "ba_eval_edges", "ba_schur_apply", "ba_set_timing", "ba_reset_stats", "ba_get_stats",
-    "ba_algorithmic_bytes", "ba_stream",
+    "ba_algorithmic_bytes", "ba_stream", "ba_layout",
 ]
 
 
@@ -100,6 +100,37 @@ def partition_points(pt_degree: np.ndarray, world_size: int) -> np.ndarray:
                                     out.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError(f"ba_partition_points failed: {rc}")
+    return out
+
+
+class LayoutSizes(C.Structure):
+    _fields_ = [("n_tiles", C.c_int64), ("n_slots", C.c_int64), ("n_local_edges", C.c_int64),
+                ("n_local_points", C.c_int64), ("n_chunks", C.c_int64), ("pt_begin", C.c_int64)]
+
+
+def layout(nC, nP, cam_idx, pt_idx, rank=0, world_size=1):
+    """Host-only (no GPU): the observation layout ba_create builds for (rank, world_size), as a dict of arrays."""
+    L = load()
+    cam_idx = np.ascontiguousarray(cam_idx, np.int32)
+    pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+    nE = len(cam_idx)
+    opt = Options(0, 0, 0, rank, world_size)
+    sz = LayoutSizes()
+    null = C.c_void_p(None)
+
+    def call(*arrays):
+        rc = L.ba_layout(C.byref(opt), C.c_int64(nC), C.c_int64(nP), C.c_int64(nE), C.c_void_p(cam_idx.ctypes.data),
+                         C.c_void_p(pt_idx.ctypes.data), C.byref(sz), *arrays)
+        if rc != 0:
+            raise RuntimeError(f"ba_layout failed: {rc}")
+
+    call(*([null] * 7))
+    out = dict(tile=np.zeros((sz.n_tiles, 4), np.int32), edge_of_slot=np.zeros(sz.n_slots, np.int64),
+               slot_cam=np.zeros(sz.n_slots, np.int32), slot_lp=np.zeros(sz.n_slots, np.int32),
+               pt_slot=np.zeros(sz.n_local_points, np.int32), chunk=np.zeros((sz.n_chunks, 4), np.int32),
+               cm_slot=np.zeros(sz.n_local_edges, np.int32))
+    call(*(C.c_void_p(out[k].ctypes.data) for k in ("tile", "edge_of_slot", "slot_cam", "slot_lp", "pt_slot", "chunk", "cm_slot")))
+    out["pt_begin"] = int(sz.pt_begin)
     return out
 
 

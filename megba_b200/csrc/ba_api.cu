@@ -868,6 +868,36 @@ int ba_partition_points(int64_t nP, const int64_t *pt_degree, int32_t world_size
   return ba::partition_points(nP, pt_degree, world_size, pt_begin);
 }
 
+int ba_layout(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx, const int32_t *pt_idx,
+              ba_layout_sizes *sizes, int32_t *tile, int64_t *edge_of_slot, int32_t *slot_cam, int32_t *slot_lp,
+              int32_t *pt_slot, int32_t *chunk, int32_t *cm_slot) {
+  if (!opt || (nE > 0 && (!cam_idx || !pt_idx))) return BA_ERR_ARG;
+  if (opt->world_size < 1 || opt->rank < 0 || opt->rank >= opt->world_size) return BA_ERR_ARG;
+  ba::HostGraph g;
+  std::string err;
+  const int rc = ba::build_host_graph(*opt, nC, nP, nE, cam_idx, pt_idx, g, err);
+  if (rc != BA_OK) return rc;
+  const size_t nSlots = (size_t)g.nSlabs * ba::TE;
+  if (sizes) {
+    sizes->n_tiles = g.nT; sizes->n_slots = (int64_t)nSlots; sizes->n_local_edges = g.nEl;
+    sizes->n_local_points = g.nPl; sizes->n_chunks = g.nChunks; sizes->pt_begin = g.pt_begin;
+  }
+  for (int t = 0; tile && t < g.nT; ++t) {
+    tile[4 * t] = g.tile[t].x; tile[4 * t + 1] = g.tile[t].y; tile[4 * t + 2] = g.tile[t].z; tile[4 * t + 3] = g.tile[t].w;
+  }
+  for (size_t i = 0; i < nSlots; ++i) {
+    if (edge_of_slot) edge_of_slot[i] = g.edge_of_slot[i];
+    if (slot_cam) slot_cam[i] = g.e_cam[i];
+    if (slot_lp) slot_lp[i] = g.e_lp[i];
+  }
+  for (int p = 0; pt_slot && p < g.nPl; ++p) pt_slot[p] = g.pt_slot[p];
+  for (int k = 0; chunk && k < g.nChunks; ++k) {
+    chunk[4 * k] = g.chunk[k].x; chunk[4 * k + 1] = g.chunk[k].y; chunk[4 * k + 2] = g.chunk[k].z; chunk[4 * k + 3] = g.chunk[k].w;
+  }
+  for (int k = 0; cm_slot && k < g.nEl; ++k) cm_slot[k] = g.cm_slot[k];
+  return BA_OK;
+}
+
 int ba_create(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx,
               const int32_t *pt_idx, const void *obs, ba_solver **out) {
   if (!opt || !out || (nE > 0 && (!cam_idx || !pt_idx || !obs))) return BA_ERR_ARG;
