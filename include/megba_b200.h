@@ -197,7 +197,11 @@ int ba_grad_inf_norm(ba_solver *s, double *g_inf);
 
 /* LMAlgo::solveCUDA (src/algo/lm_algo.cu:139-223) on top of the calls above.
  * trace may be NULL; at most trace_cap rows are written, *n_trace = rows produced.
- * verbose != 0 prints the reference's console trace.                               */
+ * verbose != 0 prints the reference's console trace.
+ * Two guards the reference lacks: a non-finite gain ratio (model decrease rounding to 0 at a
+ * converged point) counts as a fully successful step, and the trust region is kept inside
+ * [1e-20, 1e20] (the reference lets it underflow to 0 after ~45 consecutive rejections and
+ * then damps with inf); neither can change an iteration the reference completes sanely.    */
 int ba_lm_solve(ba_solver *s, const ba_lm_options *lm, const ba_pcg_options *pcg,
                 ba_lm_trace *trace, int32_t trace_cap, int32_t *n_trace, int32_t verbose);
 

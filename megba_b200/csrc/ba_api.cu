@@ -987,6 +987,9 @@ int ba_set_timing(ba_solver *s, int32_t on) {
 void *ba_stream(ba_solver *s) { return s ? (void *)s->impl->stream : nullptr; }
 
 // LMAlgo::solveCUDA, src/algo/lm_algo.cu:139-223 (line numbers in comments below)
+// Trust-region bounds of ba_lm_solve (the reference has none; see the reject branch).
+static constexpr double kMinRegion = 1e-20, kMaxRegion = 1e20;
+
 int ba_lm_solve(ba_solver *s, const ba_lm_options *lm, const ba_pcg_options *pcg, ba_lm_trace *trace,
                 int32_t trace_cap, int32_t *n_trace, int32_t verbose) {
   if (!s || !lm || !pcg) return BA_ERR_ARG;
@@ -1036,6 +1039,7 @@ int ba_lm_solve(ba_solver *s, const ba_lm_options *lm, const ba_pcg_options *pcg
         // region to 0 or NaN and damp with inf.  Treat a non-finite ratio as a fully successful step instead.
         const double f = std::max(1. / 3., 1. - std::pow(2. * rho - 1., 3));
         region /= std::isfinite(f) && f > 0. ? f : 1. / 3.;
+        region = std::min(region, kMaxRegion);  // 1 + 1/region == 1 long before this in either precision
       }
       v = 2.;
       recover = false;
@@ -1049,6 +1053,10 @@ int ba_lm_solve(ba_solver *s, const ba_lm_options *lm, const ba_pcg_options *pcg
       F_new = F;                                                              // :210
       region /= v;                                                            // :211
       v *= 2.;
+      // After ~45 consecutive rejections (a converged problem driven on with epsilon1 = epsilon2 = 0) the reference's
+      // region underflows to 0 and it damps with inf.  Keep both finite; the bounds cannot change an accepted step.
+      region = std::max(region, kMinRegion);
+      v = std::min(v, 1e300);
       recover = true;
       // H and g are untouched by our solve, so nothing else needs restoring
       m->linearized = true;
