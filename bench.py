@@ -228,7 +228,7 @@ def run_reference(args, P, dtype):
 def bench_config(args, P):
     return {"workload": f"{P.label} ({P.nC} cameras, {P.nP} points, {P.nE} observations)",
             "compute_kind": "implicit" if args.implicit else "explicit",
-            "lm": {"tau": LM_REGION, "epsilon1": 0, "epsilon2": 0},
+            "lm": {"tau": LM_REGION, "epsilon1": -1e-300, "epsilon2": -1, "note": "negative: both stopping tests disabled, exactly `steps` iterations"},
             "pcg": {"iters_per_lm_iter": args.pcg_iters, "tol": 0, "refuse_ratio": "inf"},
             "parallelism": f"point-sharded edges x{args.gpus}, cameras replicated",
             "l2": "working set per PCG iteration (>1 GB) exceeds the 126 MB L2; no explicit flush"}
@@ -277,7 +277,8 @@ def run_ours(args, P, dtype):
     cam_out = torch.empty_like(cam_in).pin_memory()
     pt_out = torch.empty_like(pt_in).pin_memory()
     stream = torch.cuda.ExternalStream(S.stream())
-    kw = dict(initial_region=LM_REGION, eps1=0.0, eps2=0.0, pcg_max_iter=args.pcg_iters, pcg_tol=0.0,
+    # negative epsilons: `||dx|| <= eps2 (||x|| + eps1)` and `||g||_inf <= eps1` can never fire, so exactly K iterations run
+    kw = dict(initial_region=LM_REGION, eps1=-1e-300, eps2=-1.0, pcg_max_iter=args.pcg_iters, pcg_tol=0.0,
               pcg_refuse=1e300)
 
     # ---------------- resident arm: K iterations in one ba_lm_solve call
