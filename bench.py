@@ -206,7 +206,7 @@ def run_reference(args, P, dtype):
     line = {
         "impl": "reference", "metric": "lm_iters_per_sec", "value": value, "unit": "LM it/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": data_label(P),
         "config": bench_config(args, P),
         "pcg_iters_per_sec": None,
         "cpu_baseline": {"value": value, "unit": "LM it/s", "cores": threads, "kind": "port", "sample": sample},
@@ -223,6 +223,23 @@ def run_reference(args, P, dtype):
         except Exception as exc:  # optional extra
             line["reference_gpu_solver"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
+
+
+def load_workload(name):
+    """The real BAL file when $BAL_DIR holds it (problem-<nC>-<nP>-pre.txt); otherwise the
+    synthetic problem of the same shape.  The JSON line's `data` / `config.workload` say which one ran."""
+    from megba_b200.synthetic import BAL_SHAPES, make_named, read_bal
+    bal_dir = os.environ.get("BAL_DIR")
+    if bal_dir and name in BAL_SHAPES:
+        nC, nP, _ = BAL_SHAPES[name]
+        path = os.path.join(bal_dir, f"problem-{nC}-{nP}-pre.txt")
+        if os.path.exists(path):
+            return read_bal(path)
+    return make_named(name)
+
+
+def data_label(P):
+    return "bal" if P.label.startswith("bal:") else "synthetic"
 
 
 def bench_config(args, P):
@@ -381,7 +398,7 @@ def run_ours(args, P, dtype):
         line = {
             "metric": "lm_iters_per_sec", "value": lm_rate, "unit": "LM it/s", "n_gpus": ws, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": data_label(P),
             "config": bench_config(args, P),
             "pcg_iters_per_sec": pcg_rate, "pcg_iters_timed": st["pcg_iters"],
             "accepted_steps": sum(1 for t in trace[1:] if t["accepted"] == 1),
@@ -402,8 +419,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference" and rank != 0:
         return  # rank 0 alone runs the CPU arm
-    from megba_b200.synthetic import make_named
-    P = make_named(args.workload)
+    P = load_workload(args.workload)
     if args.impl == "reference":
         run_reference(args, P, dtype)
     else:
