@@ -29,6 +29,32 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def physical_cores():
+    """Physical cores this process may run on (SMT siblings counted once); the CPU arms use exactly this many threads."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        allowed = list(range(os.cpu_count() or 1))
+    seen = set()
+    for c in allowed:
+        base = f"/sys/devices/system/cpu/cpu{c}/topology/"
+        try:
+            with open(base + "core_id") as f1, open(base + "physical_package_id") as f2:
+                seen.add((f2.read().strip(), f1.read().strip()))
+        except OSError:
+            seen.add(("?", str(c)))
+    return max(1, len(seen))
+
+
+# The CPU arms (oracle port) run on all physical cores with threads pinned, whatever the launcher exported
+# (torch.distributed.run sets OMP_NUM_THREADS=1).  libgomp reads these once, when the first OpenMP library loads.
+CPU_THREADS = physical_cores()
+os.environ["OMP_NUM_THREADS"] = str(CPU_THREADS)
+os.environ["OMP_PROC_BIND"] = "close"
+os.environ["OMP_PLACES"] = "cores"
+os.environ.setdefault("OMP_DYNAMIC", "false")
+
 import numpy as np  # noqa: E402
 
 WORKLOAD = "venice-1778"
@@ -101,16 +127,57 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_lm_iteration(P, pcg_iters, implicit, dtype):
-    """One LM iteration (incl. the start linearisation) of the CPU oracle; returns seconds, pcg iters, threads."""
-    from oracle.oracle import Oracle
-    O = Oracle(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype)
-    x0 = P.x(dtype)
-    t0 = time.perf_counter()
-    _, _, tr = O.lm_solve(x0, implicit=implicit, lm_max_iter=1, initial_region=LM_REGION, eps1=0.0, eps2=0.0,
-                          pcg_max_iter=pcg_iters, pcg_tol=0.0, pcg_refuse=1e300)
-    dt = time.perf_counter() - t0
-    return dt, sum(t["pcg_iters"] for t in tr), O.num_threads(), tr
+class CpuArm:
+    """The oracle port (oracle/ba_oracle.c, OpenMP) timed as the CPU arm: one LM iteration of the same fixed-work
+    configuration per step (start linearisation + `pcg_iters` PCG iterations + trial evaluation + re-linearisation),
+    CPU_THREADS pinned threads."""
+
+    def __init__(self, P, implicit, dtype):
+        from oracle.oracle import Oracle, lib
+        lib().orc_set_num_threads(CPU_THREADS)
+        self.O = Oracle(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype)
+        self.x0 = P.x(dtype)
+        self.implicit = implicit
+        self.threads = self.O.num_threads()
+
+    def step(self, pcg_iters):
+        t0 = time.perf_counter()
+        _, _, tr = self.O.lm_solve(self.x0, implicit=self.implicit, lm_max_iter=1, initial_region=LM_REGION, eps1=0.0,
+                                   eps2=0.0, pcg_max_iter=pcg_iters, pcg_tol=0.0, pcg_refuse=1e300)
+        return time.perf_counter() - t0, sum(t["pcg_iters"] for t in tr)
+
+    def measure(self, pcg_iters, steps, warmup, budget_s):
+        """Never fewer PCG iterations per step than asked; when the budget is short, FEWER STEPS are timed (and said
+        so).  Returns None for value when not even one step fits."""
+        t_first, n_first = self.step(pcg_iters)  # warm-up 1: also tells how many steps fit
+        spent = t_first
+        if t_first > budget_s:
+            return dict(value=None, pcg=None, steps_timed=0, step_s=[t_first], spread=None, pcg_per_step=n_first,
+                        fits=False, why=f"one step takes {t_first:.1f} s > budget {budget_s:.0f} s")
+        for _ in range(max(warmup - 1, 0)):
+            if spent + 2 * t_first > budget_s:
+                break
+            spent += self.step(pcg_iters)[0]
+        times = []
+        while len(times) < steps and (not times or spent + t_first <= budget_s):
+            dt, n = self.step(pcg_iters)
+            times.append(dt)
+            spent += dt
+        # repeat until two consecutive steps agree within 10 % (host noise), budget permitting
+        while len(times) >= 2 and abs(times[-1] - times[-2]) > 0.1 * min(times[-2:]) and spent + t_first <= budget_s:
+            dt, n = self.step(pcg_iters)
+            times.append(dt)
+            spent += dt
+        t_step = statistics.median(times)
+        # PCG rate: one more step with a fifth of the PCG iterations; the difference is pure PCG time
+        pcg_rate = None
+        n_small = max(pcg_iters // 5, 1)
+        if n_small < pcg_iters and spent + t_first <= budget_s + 30:
+            dt_small, got_small = self.step(n_small)
+            if t_step > dt_small and n_first > got_small:
+                pcg_rate = (n_first - got_small) / (t_step - dt_small)
+        return dict(value=1.0 / t_step, pcg=pcg_rate, steps_timed=len(times), step_s=times,
+                    spread=(max(times) - min(times)) / t_step, pcg_per_step=n_first, fits=len(times) >= steps, why=None)
 
 
 def reference_gpu_solver(P, pcg_lo=10, pcg_hi=50, args_pcg_iters=50):
@@ -131,21 +198,29 @@ def reference_gpu_solver(P, pcg_lo=10, pcg_hi=50, args_pcg_iters=50):
     HllD, _ = O.process_diag(Hll, LM_REGION)
     del r, J
     ptr = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    counts = [10, 20, 30, 40, 50]
     out = {}
-    for n in (pcg_lo, pcg_hi) * 3:
-        dx = np.zeros(9 * P.nC + 3 * P.nP)
-        ms = C.c_double()
-        rc = L.ref_solve_timed_f64(C.c_int64(P.nC), C.c_int64(P.nP), C.c_int64(P.nE), ptr(P.cam_idx), ptr(P.pt_idx),
-                                   ptr(HppD), ptr(HllD), ptr(W), ptr(g), ptr(dx), C.c_int(n), C.c_double(0.0),
-                                   C.c_double(1e300), C.byref(ms))
-        if rc != 0:
-            return None
-        out[n] = min(out.get(n, 1e30), ms.value)
-    per_iter = (out[pcg_hi] - out[pcg_lo]) / (pcg_hi - pcg_lo)
-    res = {"pcg_iters_per_sec": 1e3 / per_iter, "ms_per_pcg_iter": per_iter,
+    for rep in range(3):
+        for n in counts:
+            dx = np.zeros(9 * P.nC + 3 * P.nP)
+            ms = C.c_double()
+            rc = L.ref_solve_timed_f64(C.c_int64(P.nC), C.c_int64(P.nP), C.c_int64(P.nE), ptr(P.cam_idx), ptr(P.pt_idx),
+                                       ptr(HppD), ptr(HllD), ptr(W), ptr(g), ptr(dx), C.c_int(n), C.c_double(0.0),
+                                       C.c_double(1e300), C.byref(ms))
+            if rc != 0:
+                return None
+            if rep > 0:  # the first sweep is warm-up (cuSPARSE buffers, clocks)
+                out[n] = min(out.get(n, 1e30), ms.value)
+    xs, ys = np.array(counts, float), np.array([out[n] for n in counts])
+    A = np.vstack([xs, np.ones_like(xs)]).T
+    (per_iter, intercept), res_, _, _ = np.linalg.lstsq(A, ys, rcond=None)
+    rms = float(np.sqrt(np.mean((A @ np.array([per_iter, intercept]) - ys) ** 2)))
+    res = {"pcg_iters_per_sec": 1e3 / per_iter, "ms_per_pcg_iter": float(per_iter), "fit_intercept_ms": float(intercept),
+           "fit_rms_residual_ms": rms,
            "solve_ms": {str(k): v for k, v in out.items()},
            "what": "reference SchurPCGSolver::solve (schur_pcg_solver.cu, cuSPARSE/cuBLAS) built for sm_100a via "
-                   "oracle/shim, same GPU and problem; best of 3 per iteration count, per-iteration time by difference"}
+                   "oracle/shim, same GPU and problem; least-squares slope of the solve time over 10..50 fixed "
+                   "iterations (best of 2 per count after a warm-up sweep)"}
     del W, Hpp, Hll, HppD, HllD
     # the reference's whole LM loop (lm_algo.cu + its kernels + its solver), same fixed-work settings as our arm
     try:
@@ -176,41 +251,27 @@ def reference_gpu_solver(P, pcg_lo=10, pcg_hi=50, args_pcg_iters=50):
 
 def run_reference(args, P, dtype):
     """CPU arm: the reference has no CPU execution path (every Device::CPU branch throws) and cannot be
-    built here (Eigen/gflags absent), so this times the oracle port of its algorithm on all host threads."""
-    sample_pcg = args.pcg_iters
-    times, pcg_total = [], 0
-    threads = 0
-    # bound the whole run to a few minutes: shrink the per-step PCG count if a step is too slow
-    dt, npcg, threads, _ = oracle_lm_iteration(P, sample_pcg, args.implicit, dtype)  # warm-up 1 (also calibrates)
-    budget = 240.0
-    total_steps = args.steps + max(args.warmup - 1, 0)
-    scale = 1.0
-    if dt * total_steps > budget and sample_pcg > 5:
-        per_pcg = dt / (sample_pcg + 12.0)  # linearisations etc. cost roughly a dozen PCG iterations
-        sample_pcg = max(5, int((budget / total_steps) / per_pcg - 12))
-        scale = None
-    for _ in range(max(args.warmup - 1, 0)):
-        oracle_lm_iteration(P, sample_pcg, args.implicit, dtype)
-    for _ in range(args.steps):
-        dt, npcg, threads, _ = oracle_lm_iteration(P, sample_pcg, args.implicit, dtype)
-        times.append(dt)
-        pcg_total += npcg
-    t_step = sum(times) / len(times)
-    if scale is None:
-        # extrapolate the sampled step to the full --pcg-iters step (PCG part scales linearly)
-        per_pcg = t_step / (sample_pcg + 12.0)
-        t_step = per_pcg * (args.pcg_iters + 12.0)
-    value = 1.0 / t_step
-    sample = (f"{args.steps} x [1 LM iteration = 2 linearisations + {sample_pcg} PCG iterations] of the same "
-              f"{P.label} problem" + ("" if scale else f", extrapolated to {args.pcg_iters} PCG iterations/step"))
+    built here (Eigen/gflags absent), so this times the oracle port of its algorithm on the host's physical cores.
+    Every timed step runs the full --pcg-iters; if K steps do not fit the time budget, fewer steps are timed."""
+    arm = CpuArm(P, args.implicit, dtype)
+    m = arm.measure(args.pcg_iters, args.steps, args.warmup, budget_s=float(os.environ.get("BA_CPU_BUDGET_S", "200")))
+    value = m["value"]
+    sample = (f"{m['steps_timed']} x [1 LM iteration = 2 linearisations + {m['pcg_per_step']} PCG iterations + trial "
+              f"evaluation] of the same {P.label} problem, median step; {arm.threads} pinned OpenMP threads "
+              f"(OMP_PROC_BIND=close, OMP_PLACES=cores)" + ("" if m["fits"] else f"; {args.steps} steps asked: {m['why'] or 'time budget'}"))
     line = {
         "impl": "reference", "metric": "lm_iters_per_sec", "value": value, "unit": "LM it/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None if value is None else 1e3 / value,
+        "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": data_label(P),
         "config": bench_config(args, P),
-        "pcg_iters_per_sec": None,
-        "cpu_baseline": {"value": value, "unit": "LM it/s", "cores": threads, "kind": "port", "sample": sample},
+        "pcg_iters_per_sec": m["pcg"],
+        "cpu_baseline": {"value": value, "unit": "LM it/s", "cores": arm.threads, "kind": "port", "sample": sample,
+                         "pcg_iters_per_sec": m["pcg"], "steps_timed": m["steps_timed"], "step_seconds": m["step_s"],
+                         "spread": m["spread"]},
         "e2e": {"value": value, "unit": "LM it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "consistency": {"fits_in_driver_run": bool(m["fits"]), "extrapolated": False, "threads": arm.threads,
+                        "host_logical_cpus": os.cpu_count()},
         "gpu_launches": 0,
         "note": "MegBA has no CPU execution path (every Device::CPU branch throws); this arm is the oracle port of its "
                 "algorithm on the host cores.  reference_gpu_solver below is MegBA's OWN CUDA code (oracle/shim build) on GPU 0.",
@@ -377,13 +438,13 @@ def run_ours(args, P, dtype):
 
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
-        dt, npcg, threads, _ = oracle_lm_iteration(P, args.pcg_iters, args.implicit, dtype)
-        dt2, npcg, threads, _ = oracle_lm_iteration(P, args.pcg_iters, args.implicit, dtype)
-        dt = min(dt, dt2)
-        cpu = {"value": 1.0 / dt, "unit": "LM it/s", "cores": threads, "kind": "port",
-               "pcg_iters_per_sec": None,
-               "sample": f"best of 2 x [1 LM iteration = 2 linearisations + {npcg} PCG iterations] of the same "
-                         f"problem, oracle port (OpenMP, {threads} threads)"}
+        arm = CpuArm(P, args.implicit, dtype)
+        m = arm.measure(args.pcg_iters, 2, 1, budget_s=float(os.environ.get("BA_CPU_BASELINE_BUDGET_S", "30")))
+        cpu = {"value": m["value"], "unit": "LM it/s", "cores": arm.threads, "kind": "port",
+               "pcg_iters_per_sec": m["pcg"], "steps_timed": m["steps_timed"], "step_seconds": m["step_s"],
+               "sample": f"median of {m['steps_timed']} x [1 LM iteration = 2 linearisations + {m['pcg_per_step']} PCG iterations] "
+                         f"of the same problem after one warm-up step, oracle port (OpenMP, {arm.threads} pinned threads)"}
+        del arm
 
     ref_gpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline and dtype == np.float64 and not args.implicit:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MEGBA_B200_ABI_VERSION 1
+#define MEGBA_B200_ABI_VERSION 2
 
 typedef enum {
   BA_OK = 0,
@@ -41,15 +41,30 @@ typedef enum { BA_F64 = 0, BA_F32 = 1 } ba_dtype;
 /* ComputeKind{EXPLICIT, IMPLICIT}, include/common.h:21 */
 typedef enum { BA_EXPLICIT = 0, BA_IMPLICIT = 1 } ba_compute_kind;
 
+/* How the observations are laid out in HBM and what the S*p pass streams per observation.
+ * 0 selects the default (ELL layout, factored stream) for both compute kinds; the other values exist for
+ * measurements and parity tests.  BA_LAYOUT_TILE stores what the compute kind names (Hpl blocks / Jacobians).   */
+typedef enum { BA_LAYOUT_AUTO = 0, BA_LAYOUT_TILE = 1, BA_LAYOUT_ELL = 2 } ba_layout_kind;
+typedef enum {
+  BA_STORE_AUTO = 0,
+  BA_STORE_W = 1,    /* 9x3 Hpl block per observation, 27 scalars (tile layout, explicit kind only)            */
+  BA_STORE_J = 2,    /* 2x12 Jacobian, 24 scalars                                                               */
+  BA_STORE_FACT = 3  /* dr/dX (2x3) + normalised image point (2), 8 scalars: W = Jc^T Omega Jp is applied through
+                        a per-camera 9x9 block-diagonal map, see ba_internal.h (ELL layout only)                */
+} ba_operator_store;
+#define BA_LAYOUT_DEFAULT BA_LAYOUT_ELL
+
 /* ProblemOption (include/common.h:44-53) restricted to what the hot path needs.
  * deviceUsed[i] becomes one solver with device = deviceUsed[i], rank = i.         */
 typedef struct {
-  int32_t dtype;        /* ba_dtype                                              */
-  int32_t compute_kind; /* ba_compute_kind                                       */
-  int32_t device;       /* CUDA ordinal                                          */
-  int32_t rank;         /* 0 .. world_size-1                                     */
-  int32_t world_size;   /* number of GPUs = ProblemOption::deviceUsed.size()     */
-  int32_t reserved[3];
+  int32_t dtype;          /* ba_dtype                                              */
+  int32_t compute_kind;   /* ba_compute_kind                                       */
+  int32_t device;         /* CUDA ordinal                                          */
+  int32_t rank;           /* 0 .. world_size-1                                     */
+  int32_t world_size;     /* number of GPUs = ProblemOption::deviceUsed.size()     */
+  int32_t layout;         /* ba_layout_kind, 0 = default                           */
+  int32_t operator_store; /* ba_operator_store, 0 = default                        */
+  int32_t reserved[1];
 } ba_options;
 
 /* SolverOption::SolverOptionPCG, include/common.h:27-33 */
@@ -129,6 +144,21 @@ int ba_layout(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const i
               const int32_t *pt_idx, ba_layout_sizes *sizes, int32_t *tile, int64_t *edge_of_slot,
               int32_t *slot_cam, int32_t *slot_lp, int32_t *pt_slot, int32_t *chunk, int32_t *cm_slot);
 
+/* The same for the ELL layout (the default).  Local points are sorted by observation count, descending ("device
+ * order"); points with more than 32 observations come first and get a warp each, the rest are cut into slices of
+ * 32 points (lane = point).  Observation r of the slice's l-th point sits in slot (row0 + r) * 32 + l; observation
+ * i of a heavy point in slot row0 * 32 + i.
+ *   warp[n_warps][4]      = {first row, rows, first point (device order), kind | points << 8}, kind 1 = heavy point
+ *   perm[n_local_points]  = local point (global id - pt_begin) at each device position
+ *   edge_of_slot / slot_cam[n_slots] = observation number (-1 padding) and camera (-1 padding) of the slot
+ *   chunk / cm_slot       = camera-major view as in ba_layout                                                  */
+typedef struct ba_ell_sizes {
+  int64_t n_warps, n_rows, n_slots, n_local_edges, n_local_points, n_chunks, pt_begin, n_heavy;
+} ba_ell_sizes;
+int ba_layout_ell(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx,
+                  const int32_t *pt_idx, ba_ell_sizes *sizes, int32_t *warp, int32_t *perm, int64_t *edge_of_slot,
+                  int32_t *slot_cam, int32_t *chunk, int32_t *cm_slot);
+
 /* BaseProblem::appendVertex/appendEdge + buildIndex (src/problem/base_problem.cpp:
  * 82-125,183-214), EdgeVector::buildPositionContainer/allocateResource
  * (src/edge/base_edge.cpp:224-262, src/edge/base_edge.cu:47-103) and
@@ -137,7 +167,8 @@ int ba_layout(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const i
  * cam_idx/pt_idx: vertex numbers of each observation (any order, every rank passes
  * the full list); obs[nE][2] in the solver dtype.
  * Limits (BA_ERR_ARG otherwise): 0 < nC < 2^24, 0 < nP <= 2^30, and fewer than 2^31
- * observation slots per rank after padding to 256-slot tiles.                      */
+ * observation slots per rank after padding (256-slot tiles / 32-slot ELL rows).
+ * PCG: max_iter < 1 behaves like 1 (the reference's do-while, schur_pcg_solver.cu:265-407).   */
 int ba_create(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE,
               const int32_t *cam_idx, const int32_t *pt_idx, const void *obs,
               ba_solver **out);
@@ -157,7 +188,10 @@ int ba_get_params(ba_solver *s, void *cam, void *pt);
 
 /* Optional per-edge 2x2 information matrices, info[nE][4] row-major
  * (BaseEdge::setInformation; JMulInfo/makeHSchurWithInfo,
- * src/edge/build_linear_system.cu:149-239).  NULL restores identity.              */
+ * src/edge/build_linear_system.cu:149-239).  NULL restores identity.  In the default
+ * layout both compute kinds honour them (H = J^T Omega J as in the reference's explicit
+ * build; its implicit build has an empty branch there, build_implicit_linear_system.cu:
+ * 272-274); the tile layout refuses them in implicit mode.                        */
 int ba_set_information(ba_solver *s, const void *info);
 
 /* HP1.  EdgeVector::forward + buildLinearSystem (src/edge/base_edge.cpp:160-163,

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libmegba_b200.so")
 
 BA_F64, BA_F32 = 0, 1
 BA_EXPLICIT, BA_IMPLICIT = 0, 1
+LAYOUT_AUTO, LAYOUT_TILE, LAYOUT_ELL = 0, 1, 2
+STORE_AUTO, STORE_W, STORE_J, STORE_FACT = 0, 1, 2, 3
 BUF_HPP, BUF_HLL, BUF_W, BUF_J, BUF_G, BUF_DX = range(6)
 
 # every symbol include/megba_b200.h declares (tests check the export list against the header)
@@ -25,13 +27,14 @@ SYMBOLS = [
     "ba_linearize", "ba_process_diag", "ba_solve", "ba_step_norms", "ba_eval_trial",
     "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
     "ba_eval_edges", "ba_schur_apply", "ba_set_timing", "ba_reset_stats", "ba_get_stats",
-    "ba_algorithmic_bytes", "ba_stream", "ba_layout",
+    "ba_algorithmic_bytes", "ba_stream", "ba_layout", "ba_layout_ell",
 ]
 
 
 class Options(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("compute_kind", C.c_int32), ("device", C.c_int32),
-                ("rank", C.c_int32), ("world_size", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("rank", C.c_int32), ("world_size", C.c_int32), ("layout", C.c_int32),
+                ("operator_store", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class PcgOptions(C.Structure):
@@ -134,6 +137,38 @@ def layout(nC, nP, cam_idx, pt_idx, rank=0, world_size=1):
     return out
 
 
+class EllSizes(C.Structure):
+    _fields_ = [("n_warps", C.c_int64), ("n_rows", C.c_int64), ("n_slots", C.c_int64), ("n_local_edges", C.c_int64),
+                ("n_local_points", C.c_int64), ("n_chunks", C.c_int64), ("pt_begin", C.c_int64), ("n_heavy", C.c_int64)]
+
+
+def layout_ell(nC, nP, cam_idx, pt_idx, rank=0, world_size=1):
+    """Host-only (no GPU): the ELL observation layout (the default of ba_create), as a dict of arrays."""
+    L = load()
+    cam_idx = np.ascontiguousarray(cam_idx, np.int32)
+    pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+    nE = len(cam_idx)
+    opt = Options(0, 0, 0, rank, world_size)
+    sz = EllSizes()
+    null = C.c_void_p(None)
+
+    def call(*arrays):
+        rc = L.ba_layout_ell(C.byref(opt), C.c_int64(nC), C.c_int64(nP), C.c_int64(nE), C.c_void_p(cam_idx.ctypes.data),
+                             C.c_void_p(pt_idx.ctypes.data), C.byref(sz), *arrays)
+        if rc != 0:
+            raise RuntimeError(f"ba_layout_ell failed: {rc}")
+
+    call(*([null] * 6))
+    out = dict(warp=np.zeros((sz.n_warps, 4), np.int32), perm=np.zeros(sz.n_local_points, np.int32),
+               edge_of_slot=np.zeros(sz.n_slots, np.int64), slot_cam=np.zeros(sz.n_slots, np.int32),
+               chunk=np.zeros((sz.n_chunks, 4), np.int32), cm_slot=np.zeros(sz.n_local_edges, np.int32))
+    call(*(C.c_void_p(out[k].ctypes.data) for k in ("warp", "perm", "edge_of_slot", "slot_cam", "chunk", "cm_slot")))
+    out["pt_begin"] = int(sz.pt_begin)
+    out["n_heavy"] = int(sz.n_heavy)
+    out["n_rows"] = int(sz.n_rows)
+    return out
+
+
 def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
@@ -142,13 +177,13 @@ class Solver:
     """Thin owner of one ba_solver handle; method names follow the C-ABI."""
 
     def __init__(self, nC, nP, cam_idx, pt_idx, obs, dtype=np.float64, implicit=False, device=0, rank=0,
-                 world_size=1):
+                 world_size=1, layout=LAYOUT_AUTO, store=STORE_AUTO):
         self.L = load()
         self.dtype = np.dtype(dtype)
         self.nC, self.nP, self.nE = int(nC), int(nP), int(len(cam_idx))
         self.implicit = bool(implicit)
         opt = Options(BA_F64 if self.dtype == np.float64 else BA_F32, BA_IMPLICIT if implicit else BA_EXPLICIT,
-                      device, rank, world_size)
+                      device, rank, world_size, layout, store)
         cam_idx = np.ascontiguousarray(cam_idx, dtype=np.int32)
         pt_idx = np.ascontiguousarray(pt_idx, dtype=np.int32)
         obs = np.ascontiguousarray(obs, dtype=self.dtype)

@@ -56,7 +56,35 @@ struct HostGraph {
   std::vector<int> cam_chunk_ptr;
   std::vector<int> cm_pt;
   std::vector<int> cm_slot;            // slot of each camera-major entry
+  std::vector<int64_t> cuts;           // point cuts of all ranks [world_size + 1]
+  // ELL layout (ba_internal.h): device order = local points sorted by observation count, descending
+  bool ell = false;
+  int nW = 0, nRows = 0, nHeavy = 0;
+  std::vector<int4> wdesc;             // {first row, rows, first point (device order), kind | np << 8}
+  std::vector<int> perm;               // device position -> local point
 };
+
+// ba_options::layout / operator_store (0 = auto) and the BA_LAYOUT / BA_STORE environment overrides (experiments).
+static int resolve_layout(const ba_options &opt, int *layout, int *store) {
+  int l = opt.layout, st = opt.operator_store;
+  if (const char *e = getenv("BA_LAYOUT")) l = !strcmp(e, "tile") ? BA_LAYOUT_TILE : !strcmp(e, "ell") ? BA_LAYOUT_ELL : l;
+  if (const char *e = getenv("BA_STORE")) st = !strcmp(e, "w") ? BA_STORE_W : !strcmp(e, "j") ? BA_STORE_J : !strcmp(e, "fact") ? BA_STORE_FACT : st;
+  if (l == 0) l = (st == BA_STORE_W) ? BA_LAYOUT_TILE : BA_LAYOUT_DEFAULT;
+  if (l == BA_LAYOUT_TILE) {
+    // the tile layout stores what the compute kind says: Hpl blocks (explicit) or Jacobians (implicit)
+    const int want = opt.compute_kind == BA_IMPLICIT ? BA_STORE_J : BA_STORE_W;
+    if (st != 0 && st != want) return BA_ERR_ARG;
+    st = want;
+  } else if (l == BA_LAYOUT_ELL) {
+    if (st == 0) st = BA_STORE_FACT;
+    if (st == BA_STORE_W) return BA_ERR_ARG;
+  } else {
+    return BA_ERR_ARG;
+  }
+  *layout = l;
+  *store = st == BA_STORE_W ? ST_W : st == BA_STORE_J ? ST_J : ST_FACT;
+  return BA_OK;
+}
 
 static int partition_points(int64_t nP, const int64_t *deg, int ws, int64_t *cuts) {
   if (nP < 0 || ws < 1 || !cuts || (nP > 0 && !deg)) return BA_ERR_ARG;
@@ -70,6 +98,85 @@ static int partition_points(int64_t nP, const int64_t *deg, int ws, int64_t *cut
     cuts[r] = p;
   }
   cuts[ws] = nP;
+  return BA_OK;
+}
+
+// Camera-major view shared by both layouts: entries of a camera in ascending slot order, cut into chunks.
+static void build_camera_major(int64_t nC, size_t nSlots, HostGraph &g) {
+  std::vector<int> cptr(nC + 1, 0);
+  for (size_t s = 0; s < nSlots; ++s)
+    if (g.edge_of_slot[s] >= 0) cptr[g.e_cam[s] + 1]++;
+  for (int64_t c = 0; c < nC; ++c) cptr[c + 1] += cptr[c];
+  g.chunk.clear();
+  g.cam_chunk_ptr.assign(nC + 1, 0);
+  for (int64_t c = 0; c < nC; ++c) {
+    for (int b = cptr[c]; b < cptr[c + 1]; b += CM_CHUNK)
+      g.chunk.push_back(make_int4((int)c, b, std::min(b + CM_CHUNK, cptr[c + 1]), 0));
+    g.cam_chunk_ptr[c + 1] = (int)g.chunk.size();
+  }
+  g.nChunks = (int)g.chunk.size();
+}
+
+// ELL layout: see ba_internal.h.  ptr/order = this rank's observations grouped by local point, camera-ascending.
+static int build_ell(int64_t nC, int64_t nE, const int32_t *cam_idx, const std::vector<int64_t> &ptr,
+                     const std::vector<int64_t> &order, HostGraph &g, std::string &err) {
+  const int nPl = g.nPl;
+  g.perm.resize(nPl);
+  for (int p = 0; p < nPl; ++p) g.perm[p] = p;
+  std::stable_sort(g.perm.begin(), g.perm.end(), [&](int a, int b) { return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b]; });
+  auto deg = [&](int k) { return ptr[g.perm[k] + 1] - ptr[g.perm[k]]; };
+  g.wdesc.clear();
+  int64_t rows = 0;
+  int k = 0;
+  for (; k < nPl && deg(k) > ELL_HEAVY; ++k) {  // heavy points: one warp each, lane = observation
+    const int64_t D = (deg(k) + 31) / 32;
+    g.wdesc.push_back(make_int4((int)rows, (int)D, k, 1 | (1 << 8)));
+    rows += D;
+    if (rows * 32 >= (1ll << 31)) { err = "too many observation slots on one rank"; return BA_ERR_ARG; }
+  }
+  g.nHeavy = k;
+  for (; k < nPl; k += 32) {  // slices of 32 points, lane = point; sorted, so deg(k) is the largest of the slice
+    const int np = std::min(32, nPl - k);
+    const int64_t D = deg(k);
+    g.wdesc.push_back(make_int4((int)rows, (int)D, k, 0 | (np << 8)));
+    rows += D;
+    if (rows * 32 >= (1ll << 31)) { err = "too many observation slots on one rank"; return BA_ERR_ARG; }
+  }
+  g.nW = (int)g.wdesc.size();
+  g.nRows = (int)rows;
+  const size_t nSlots = (size_t)rows * 32;
+  g.e_cam.assign(nSlots, -1);
+  g.edge_of_slot.assign(nSlots, -1);
+  g.slot_of_edge.assign(nE, -1);
+  g.cm_pt.assign(g.nEl, 0);
+  g.cm_slot.assign(g.nEl, 0);
+  std::vector<int> slot_pt(nSlots, 0);
+  for (const int4 &wd : g.wdesc) {
+    const bool heavy = (wd.w & 0xff) != 0;
+    const int np = wd.w >> 8;
+    for (int l = 0; l < (heavy ? 1 : np); ++l) {
+      const int kd = wd.z + l, pn = g.perm[kd];
+      for (int64_t i = 0; i < ptr[pn + 1] - ptr[pn]; ++i) {
+        const size_t slot = heavy ? ((size_t)wd.x + i / 32) * 32 + i % 32 : ((size_t)wd.x + i) * 32 + l;
+        const int64_t e = order[ptr[pn] + i];
+        g.e_cam[slot] = cam_idx[e];
+        g.edge_of_slot[slot] = e;
+        g.slot_of_edge[e] = (int32_t)slot;
+        slot_pt[slot] = kd;
+      }
+    }
+  }
+  build_camera_major(nC, nSlots, g);
+  {
+    std::vector<int> cf(nC, 0);
+    for (int64_t c = 0; c < nC; ++c) cf[c] = g.chunk.empty() || g.cam_chunk_ptr[c] == g.cam_chunk_ptr[c + 1] ? 0 : g.chunk[g.cam_chunk_ptr[c]].y;
+    for (size_t s = 0; s < nSlots; ++s) {
+      if (g.edge_of_slot[s] < 0) continue;
+      const int kk = cf[g.e_cam[s]]++;
+      g.cm_pt[kk] = slot_pt[s];
+      g.cm_slot[kk] = (int)s;
+    }
+  }
   return BA_OK;
 }
 
@@ -102,6 +209,8 @@ static int build_host_graph(const ba_options &opt, int64_t nC, int64_t nP, int64
     std::sort(order.begin() + ptr[p], order.begin() + ptr[p + 1], [&](int64_t a, int64_t b) {
       return cam_idx[a] != cam_idx[b] ? cam_idx[a] < cam_idx[b] : a < b;
     });
+  g.cuts = cuts;
+  if (g.ell) return build_ell(nC, nE, cam_idx, ptr, order, g, err);
   // tiles
   g.tile.clear();
   g.pt_slot.assign(g.nPl, 0);
@@ -202,6 +311,7 @@ struct Impl {
   ba_stats stats{};
   bool linearized = false;
   double region = 1e3;
+  int store_cfg = ST_W;  // configured operator stream; Dev::store is the one in effect for the current linearisation
   virtual ~Impl() {}
   int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -242,6 +352,10 @@ struct ImplT : Impl {
   size_t arena_bytes = 0;
   T *e_info_dev = nullptr, *cm_info_dev = nullptr;
   T *pt_full = nullptr;  // [3 nP] gather buffer, world_size > 1 only
+  // ELL layout
+  int *perm_dev = nullptr; // [nPl] device position -> local point
+  T *pt_nat = nullptr;     // [3 nPl] staging in the caller's point order
+  T *r_info_dev = nullptr;
   double *h_scal = nullptr;
   PcgState *h_st = nullptr;  // two pinned slots (chunk k is polled while chunk k+1 runs)
   cudaEvent_t st_event[2] = {nullptr, nullptr};
@@ -262,6 +376,7 @@ struct ImplT : Impl {
     if (arena) cudaFree(arena);
     if (e_info_dev) cudaFree(e_info_dev);
     if (cm_info_dev) cudaFree(cm_info_dev);
+    if (r_info_dev) cudaFree(r_info_dev);
     if (pt_full) cudaFree(pt_full);
     for (auto *q : ipc_opened) if (q) cudaIpcCloseMemHandle(q);
     if (xchg) cudaFree(xchg);
@@ -383,22 +498,30 @@ struct ImplT : Impl {
     const T *obs = (const T *)obs_v;
     BA_CUDA(cudaSetDevice(opt.device));
     BA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    const int K = opt.compute_kind == BA_IMPLICIT ? 24 : 27;
-    const size_t nSlots = (size_t)g.nSlabs * TE, nC = g.nC, nPl = g.nPl, nEl = g.nEl;
-    const size_t nPart = std::max<size_t>({(size_t)g.nT * 2, (size_t)AUX_GRID * 4, 64});
+    const bool ell = g.ell;
+    const int K = ell ? 24 : (opt.compute_kind == BA_IMPLICIT ? 24 : 27);  // ELL: room for the Jacobian stream (small-angle cameras)
+    const size_t nSlots = ell ? (size_t)g.nRows * 32 : (size_t)g.nSlabs * TE, nC = g.nC, nPl = g.nPl, nEl = g.nEl;
+    const size_t nPlPad = (nPl + 255) / 256 * 256;
+    const size_t nPart = std::max<size_t>({(size_t)g.nT * 2, (size_t)g.nW * 2, (size_t)AUX_GRID * 4, 64});
     // arena carving
     struct Item { void **ptr; size_t bytes; };
     std::vector<Item> items;
     int4 *tile, *chunk; int *e_cam, *pt_slot, *cam_chunk_ptr, *cm_pt; unsigned short *e_lp; T *e_obs, *cm_obs;
     auto add = [&](auto **p, size_t count) { items.push_back({(void **)p, count * sizeof(**p)}); };
-    add(&tile, g.nT); add(&e_cam, nSlots); add(&e_lp, nSlots); add(&e_obs, 2 * nSlots); add(&pt_slot, nPl);
+    int4 *wdesc = nullptr;
+    add(&tile, g.nT); add(&e_cam, nSlots); add(&e_lp, ell ? 0 : nSlots); add(&e_obs, 2 * nSlots); add(&pt_slot, ell ? 0 : nPl);
+    if (ell) {
+      add(&wdesc, g.nW); add(&d.camc, (size_t)CAMC * nC); add(&d.camT, (size_t)CAMT * nC);
+      add(&d.HllInvP, 9 * nPlPad); add(&d.wP, 3 * nPlPad); add(&d.XP, 3 * nPlPad);
+      add(&perm_dev, nPl); add(&pt_nat, 3 * nPl);
+    }
     add(&chunk, g.nChunks); add(&cam_chunk_ptr, nC + 1); add(&cm_pt, nEl); add(&cm_obs, 2 * nEl);
     add(&d.cam, 9 * nC); add(&d.pt, 3 * nPl);
     add(&d.Hpp, 90 * nC);  // Hpp followed by gc
     add(&d.Hll, 9 * nPl); add(&d.gl, 3 * nPl);
     add(&d.WJ, (size_t)K * nSlots);
     add(&d.cm_part, (size_t)g.nChunks * 54);
-    add(&d.HppD, 81 * nC); add(&d.HppInv, 81 * nC); add(&d.HllInv, 9 * nPl); add(&d.w, 3 * nPl);
+    add(&d.HppD, 81 * nC); add(&d.HppInv, 81 * nC); add(&d.HllInv, ell ? 0 : 9 * nPl); add(&d.w, ell ? 0 : 3 * nPl);
     add(&d.dxc, 9 * nC); add(&d.dxl, 3 * nPl); add(&d.dxc_bk, 9 * nC); add(&d.dxl_bk, 3 * nPl);
     add(&d.sA, 3 * (size_t)NREP * 9 * nC);  // sA[NREP][9nC] followed by sB[2][NREP][9nC]
     add(&d.r, 9 * nC); add(&d.p, 9 * nC); add(&d.q, 9 * nC); add(&d.z, 9 * nC); add(&d.xbk, 9 * nC);
@@ -418,6 +541,14 @@ struct ImplT : Impl {
     d.sB = d.sA + (size_t)NREP * 9 * nC;
     d.nC = (int)nC; d.nPl = (int)nPl; d.nT = g.nT; d.nSlabs = g.nSlabs; d.nChunks = g.nChunks; d.nEl = g.nEl;
     d.implicit = opt.compute_kind == BA_IMPLICIT;
+    d.ell = ell; d.nW = g.nW; d.nRows = g.nRows; d.nPlPad = (int)nPlPad;
+    d.wdesc = wdesc; d.r_cam = e_cam; d.r_obs = e_obs; d.r_info = nullptr;
+    if (ell) {
+      // the factored stream needs the register-resident camera kernel (it applies T_c / T_c^T)
+      if (store_cfg == ST_FACT && !pcg_reg_kernel_available<T>(d)) store_cfg = ST_J;
+      d.implicit = 1;  // nothing in the ELL path materialises Hpl
+    }
+    d.store = store_cfg;
     d.tile = tile; d.e_cam = e_cam; d.e_lp = e_lp; d.e_obs = e_obs; d.e_info = nullptr; d.pt_slot = pt_slot;
     d.chunk = chunk; d.cam_chunk_ptr = cam_chunk_ptr; d.cm_pt = cm_pt; d.cm_obs = cm_obs; d.cm_info = nullptr;
     d.damp = 1. / region;
@@ -437,9 +568,14 @@ struct ImplT : Impl {
     };
     BA_CUDA(up(tile, g.tile.data(), sizeof(int4) * g.nT));
     BA_CUDA(up(e_cam, g.e_cam.data(), sizeof(int) * nSlots));
-    BA_CUDA(up(e_lp, g.e_lp.data(), sizeof(unsigned short) * nSlots));
     BA_CUDA(up(e_obs, h_obs.data(), sizeof(T) * 2 * nSlots));
-    BA_CUDA(up(pt_slot, g.pt_slot.data(), sizeof(int) * nPl));
+    if (ell) {
+      BA_CUDA(up(wdesc, g.wdesc.data(), sizeof(int4) * g.nW));
+      BA_CUDA(up(perm_dev, g.perm.data(), sizeof(int) * nPl));
+    } else {
+      BA_CUDA(up(e_lp, g.e_lp.data(), sizeof(unsigned short) * nSlots));
+      BA_CUDA(up(pt_slot, g.pt_slot.data(), sizeof(int) * nPl));
+    }
     BA_CUDA(up(chunk, g.chunk.data(), sizeof(int4) * g.nChunks));
     BA_CUDA(up(cam_chunk_ptr, g.cam_chunk_ptr.data(), sizeof(int) * (nC + 1)));
     BA_CUDA(up(cm_pt, g.cm_pt.data(), sizeof(int) * nEl));
@@ -462,8 +598,11 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     const T *cam = (const T *)cam_v, *pt = (const T *)pt_v;
     BA_CUDA(cudaMemcpyAsync(d.cam, cam, sizeof(T) * 9 * g.nC, cudaMemcpyHostToDevice, stream));
-    if (g.nPl)
-      BA_CUDA(cudaMemcpyAsync(d.pt, pt + 3 * g.pt_begin, sizeof(T) * 3 * g.nPl, cudaMemcpyHostToDevice, stream));
+    if (g.nPl) {
+      BA_CUDA(cudaMemcpyAsync(g.ell ? pt_nat : d.pt, pt + 3 * g.pt_begin, sizeof(T) * 3 * g.nPl, cudaMemcpyHostToDevice, stream));
+      if (g.ell) BA_CUDA(launch_permute3<T>(pt_nat, d.pt, perm_dev, g.nPl, 1, stream));
+    }
+    if (g.ell) { BA_CUDA(launch_cam_consts<T>(d, stream)); stats.launches += g.nPl ? 2 : 1; }
     // a new parameter vector is a new problem: deltaX starts at zero (allocateResourceCUDA memset,
     // schur_LM_linear_system.cu:37)
     BA_CUDA(cudaMemsetAsync(d.dxc, 0, sizeof(T) * 9 * g.nC, stream));
@@ -482,14 +621,25 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     T *cam = (T *)cam_v, *pt = (T *)pt_v;
     BA_CUDA(cudaMemcpyAsync(cam, d.cam, sizeof(T) * 9 * g.nC, cudaMemcpyDeviceToHost, stream));
+    const T *own = d.pt;  // this rank's points in the caller's order
+    if (g.ell && g.nPl) {
+      BA_CUDA(launch_permute3<T>(d.pt, pt_nat, perm_dev, g.nPl, 0, stream));
+      stats.launches += 1;
+      own = pt_nat;
+    }
     if (opt.world_size == 1) {
-      BA_CUDA(cudaMemcpyAsync(pt, d.pt, sizeof(T) * 3 * g.nP, cudaMemcpyDeviceToHost, stream));
+      BA_CUDA(cudaMemcpyAsync(pt, own, sizeof(T) * 3 * g.nP, cudaMemcpyDeviceToHost, stream));
     } else {
-      // every rank owns a contiguous point range: zero-fill + allreduce(sum) = allgatherv
-      BA_CUDA(cudaMemsetAsync(pt_full, 0, sizeof(T) * 3 * g.nP, stream));
+      // every rank owns a contiguous point range: an all-gather with per-rank counts = one broadcast per rank, grouped
+      if (!comm_ready) return fail(BA_ERR_STATE, "world_size > 1 but ba_comm_init was not called");
       if (g.nPl)
-        BA_CUDA(cudaMemcpyAsync(pt_full + 3 * g.pt_begin, d.pt, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
-      BA_TRY(allreduce_T(pt_full, 3 * (size_t)g.nP));
+        BA_CUDA(cudaMemcpyAsync(pt_full + 3 * g.pt_begin, own, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
+      BA_NCCL(ncclGroupStart());
+      for (int r = 0; r < opt.world_size; ++r) {
+        const size_t cnt = 3 * (size_t)(g.cuts[r + 1] - g.cuts[r]);
+        if (cnt) BA_NCCL(ncclBroadcast(pt_full + 3 * g.cuts[r], pt_full + 3 * g.cuts[r], cnt, NcclType<T>::v, r, comm, stream));
+      }
+      BA_NCCL(ncclGroupEnd());
       BA_CUDA(cudaMemcpyAsync(pt, pt_full, sizeof(T) * 3 * g.nP, cudaMemcpyDeviceToHost, stream));
     }
     BA_CUDA(cudaStreamSynchronize(stream));
@@ -500,7 +650,35 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     if (!info_v) {
       d.e_info = nullptr;
+      d.r_info = nullptr;
       d.cm_info = nullptr;
+      linearized = false;
+      return BA_OK;
+    }
+    if (g.ell) {
+      // Both compute kinds apply W = Jc^T Omega Jp through the stored factors, so information matrices work in
+      // implicit mode too (upstream's implicit build has an empty branch there, build_implicit_linear_system.cu:272-274;
+      // the semantics chosen here are those of its explicit build, build_linear_system.cu:149-239).
+      const T *info = (const T *)info_v;
+      const size_t nSlots = (size_t)g.nRows * 32, nEl = g.nEl;
+      std::vector<T> h_e(4 * nSlots, T(0)), h_c(4 * nEl);
+      for (size_t sl = 0; sl < nSlots; ++sl) {
+        const int64_t e = g.edge_of_slot[sl];
+        if (e >= 0) for (int k = 0; k < 4; ++k) h_e[4 * sl + k] = info[4 * e + k];
+      }
+      for (size_t k = 0; k < nEl; ++k) {
+        const int64_t e = g.edge_of_slot[g.cm_slot[k]];
+        for (int q = 0; q < 4; ++q) h_c[4 * k + q] = info[4 * e + q];
+      }
+      if (!r_info_dev) {
+        BA_CUDA(cudaMalloc(&r_info_dev, sizeof(T) * std::max<size_t>(4 * nSlots, 4)));
+        BA_CUDA(cudaMalloc(&cm_info_dev, sizeof(T) * std::max<size_t>(4 * nEl, 4)));
+      }
+      BA_CUDA(cudaMemcpyAsync(r_info_dev, h_e.data(), sizeof(T) * 4 * nSlots, cudaMemcpyHostToDevice, stream));
+      BA_CUDA(cudaMemcpyAsync(cm_info_dev, h_c.data(), sizeof(T) * 4 * nEl, cudaMemcpyHostToDevice, stream));
+      BA_CUDA(cudaStreamSynchronize(stream));
+      d.r_info = r_info_dev;
+      d.cm_info = cm_info_dev;
       linearized = false;
       return BA_OK;
     }
@@ -536,14 +714,22 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     size_t ev = 0;
     if (timing) ev = ev_begin();
-    BA_CUDA(launch_linearize<T>(d, stream));
-    stats.launches += launches_of_linearize();
+    if (g.ell) {
+      d.store = store_cfg;  // the launcher wants the configured store; the one in effect is known after the fetch below
+      BA_CUDA(launch_linearize_ell<T>(d, stream));
+      stats.launches += launches_of_linearize_ell() - (store_cfg == ST_FACT ? 0 : 1);
+    } else {
+      BA_CUDA(launch_linearize<T>(d, stream));
+      stats.launches += launches_of_linearize();
+    }
     stats.linearize_calls += 1;
     BA_TRY(allreduce_T(d.Hpp, 90 * (size_t)g.nC));
     BA_TRY(allreduce_scal(S_COST, 1, ncclSum));
     if (timing) { ev_end(ev); ev_lin.push_back(ev); }
     BA_TRY(fetch_scalars());
     if (cost) *cost = h_scal[S_COST];
+    // a camera in the small-angle branch (theta^2 <= eps) makes this linearisation stream the Jacobian instead
+    if (g.ell) d.store = (store_cfg == ST_FACT && h_scal[S_ANY_SMALL] == 0.) ? ST_FACT : ST_J;
     linearized = true;
     return BA_OK;
   }
@@ -559,10 +745,25 @@ struct ImplT : Impl {
   int schur_edge(int mode, const T *xin, T *sout, int check_active, bool timed, T *zero_set = nullptr) {
     size_t ev = 0;
     if (timing && timed) ev = ev_begin();
-    BA_CUDA(launch_schur_edge<T>(d, mode, xin, sout, zero_set, check_active, stream));
+    if (g.ell) BA_CUDA(launch_schur_ell<T>(d, mode, xin, sout, zero_set, check_active, stream));
+    else BA_CUDA(launch_schur_edge<T>(d, mode, xin, sout, zero_set, check_active, stream));
     if (timing && timed) { ev_end(ev); ev_schur.push_back(ev); }
-    stats.launches += d.nT > 0 ? 1 : 0;
+    stats.launches += (d.nT > 0 || d.nW > 0) ? 1 : 0;
     if (timed) stats.schur_apply_calls += 1;
+    return BA_OK;
+  }
+
+  // block inverses (+ w, plane copies) and the padded / transformed copy of a camera vector the edge pass gathers
+  int prep() {
+    if (g.ell) { BA_CUDA(launch_prep_ell<T>(d, stream)); BA_CUDA(launch_prep<T>(d, stream)); }
+    else BA_CUDA(launch_prep<T>(d, stream));
+    stats.launches += launches_of_prep();
+    return BA_OK;
+  }
+  int pad_cam(const T *src) {
+    if (d.store == ST_FACT) BA_CUDA(launch_pad_cam_T<T>(d, src, stream));
+    else BA_CUDA(launch_pad_cam<T>(d, src, stream));
+    stats.launches += 1;
     return BA_OK;
   }
 
@@ -572,6 +773,7 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     size_t ev_s = 0, ev_p = 0;
     if (timing) ev_s = ev_begin();
+    const int max_iter = std::max(1, (int)o->max_iter);  // the reference's do-while always runs its first iteration
     const bool multi = opt.world_size > 1;
     // multi-GPU: either the fused peer-memory exchange inside the camera kernel, or fold + NCCL allreduce
     static const bool no_p2p_env = getenv("BA_NO_P2P") != nullptr;
@@ -581,14 +783,19 @@ struct ImplT : Impl {
     if (!fused) pxl.ws = 1;
     auto next_epoch = [&]() { if (fused) { pxl.epoch = ++px_epoch; pxl.parity = (int)(px_epoch & 1); } };
     BA_CUDA(cudaMemsetAsync(d.sA, 0, sizeof(T) * 3 * NREP * 9 * g.nC, stream));
+    if (fused) {
+      // a time-out of an earlier solve must not poison this one, and no rank may start publishing into an exchange
+      // buffer that a slower peer is still reading in the last iteration of ITS previous solve: one tiny allreduce
+      // re-aligns the ranks (the fused path has no other collective between solves)
+      BA_CUDA(cudaMemsetAsync(d.scal + S_XCHG_ERR, 0, sizeof(double), stream));
+      BA_TRY(allreduce_scal(S_XCHG_ERR, 1, ncclMax));
+    }
     const size_t set_sz = (size_t)NREP * 9 * g.nC;  // sB set k lives at d.sB + k * set_sz
-    BA_CUDA(launch_prep<T>(d, stream));
-    stats.launches += launches_of_prep();
+    BA_TRY(prep());
     // MakeV and the operator application on the warm start x0 share ONE pass over W:
     //   sB = Hpl (Hll^-1 Hlp x0 - w)  so that  r0 = v - S x0 = g_c - Hpp x0 + sB   (schur_pcg_solver.cu:430-510,202-258);
     // sA (the reference's separate Hpl w) stays zero.
-    BA_CUDA(launch_pad_cam<T>(d, d.dxc, stream));
-    stats.launches += 1;
+    BA_TRY(pad_cam(d.dxc));
     BA_TRY(schur_edge(SM_INIT, d.xpad, d.sB, 0, true));
     if (multi && !fused) {
       BA_CUDA(launch_fold_replicas<T>(d, d.sA, 2, stream));
@@ -597,7 +804,7 @@ struct ImplT : Impl {
       BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
     }
     next_epoch();
-    BA_CUDA(launch_pcg_init<T>(d, d.sB, o->max_iter, o->tol, o->refuse_ratio, nrep, pxl, stream));
+    BA_CUDA(launch_pcg_init<T>(d, d.sB, max_iter, o->tol, o->refuse_ratio, nrep, pxl, stream));
     stats.launches += 1;
     if (timing) ev_p = ev_begin();
     // The loop is enqueued in chunks; the device-side `active` flag turns the remaining launches of a
@@ -613,8 +820,8 @@ struct ImplT : Impl {
       if (!hs.active) finished = true;
       return BA_OK;
     };
-    while (launched < o->max_iter && !finished) {
-      const int n = std::min(pcg_chunk, o->max_iter - launched);
+    while (launched < max_iter && !finished) {
+      const int n = std::min(pcg_chunk, max_iter - launched);
       for (int i = 0; i < n; ++i) {
         // iteration it accumulates into set (it+1)&1 and clears set it&1 (read by the previous camera kernel)
         const int it = launched + i;
@@ -658,8 +865,7 @@ struct ImplT : Impl {
     // launches issued after the loop ended returned immediately: keep only the samples of iterations that ran
     for (auto &e : loc_schur) if (e.second < h_st[0].n) ev_schur.push_back(e.first);
     for (auto &e : loc_cam) if (e.second < h_st[0].n) ev_cam.push_back(e.first);
-    BA_CUDA(launch_pad_cam<T>(d, d.dxc, stream));
-    stats.launches += 1;
+    BA_TRY(pad_cam(d.dxc));
     BA_TRY(schur_edge(SM_BACKSUB, d.xpad, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
     if (timing) { ev_end(ev_s); ev_solve.push_back(ev_s); }
     stats.pcg_iters += h_st[0].n;
@@ -681,7 +887,8 @@ struct ImplT : Impl {
 
   int eval_trial(double *cost_new, double *model_sq) override {
     BA_CUDA(cudaSetDevice(opt.device));
-    BA_CUDA(launch_trial<T>(d, stream));
+    if (g.ell) BA_CUDA(launch_trial_ell<T>(d, stream));
+    else BA_CUDA(launch_trial<T>(d, stream));
     stats.launches += 2;
     BA_TRY(allreduce_scal(S_TRIAL_COST, 2, ncclSum));
     BA_TRY(fetch_scalars());
@@ -694,6 +901,7 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     BA_CUDA(launch_apply_step<T>(d, stream));
     stats.launches += 1;
+    if (g.ell) { BA_CUDA(launch_cam_consts<T>(d, stream)); stats.launches += 1; }
     linearized = false;
     return BA_OK;
   }
@@ -728,6 +936,7 @@ struct ImplT : Impl {
     BA_CUDA(cudaSetDevice(opt.device));
     T *out = (T *)out_v;
     const size_t nC = g.nC, nP = g.nP, nPl = g.nPl, pb = g.pt_begin;
+    if (g.ell && which != BA_BUF_HPP) return read_ell(which, out);
     switch (which) {
       case BA_BUF_HPP:
         BA_CUDA(cudaMemcpyAsync(out, d.Hpp, sizeof(T) * 81 * nC, cudaMemcpyDeviceToHost, stream));
@@ -769,12 +978,74 @@ struct ImplT : Impl {
     return BA_OK;
   }
 
+  // ELL: per-point device arrays are in device order (g.perm); W / J are produced from the Jacobian kernel
+  int read_ell(int which, T *out) {
+    const size_t nC = g.nC, nP = g.nP, nPl = g.nPl, pb = g.pt_begin;
+    auto fetch_points = [&](const T *dev, int width, T *dst /* [nP][width] region start */) -> int {
+      std::vector<T> h(width * nPl);
+      if (nPl) BA_CUDA(cudaMemcpyAsync(h.data(), dev, sizeof(T) * width * nPl, cudaMemcpyDeviceToHost, stream));
+      BA_CUDA(cudaStreamSynchronize(stream));
+      for (size_t k = 0; k < nPl; ++k)
+        for (int j = 0; j < width; ++j) dst[width * (pb + g.perm[k]) + j] = h[width * k + j];
+      return BA_OK;
+    };
+    switch (which) {
+      case BA_BUF_HLL:
+        memset(out, 0, sizeof(T) * 9 * nP);
+        BA_TRY(fetch_points(d.Hll, 9, out));
+        break;
+      case BA_BUF_G:
+        memset(out, 0, sizeof(T) * (9 * nC + 3 * nP));
+        BA_CUDA(cudaMemcpyAsync(out, d.gc, sizeof(T) * 9 * nC, cudaMemcpyDeviceToHost, stream));
+        BA_TRY(fetch_points(d.gl, 3, out + 9 * nC));
+        break;
+      case BA_BUF_DX:
+        memset(out, 0, sizeof(T) * (9 * nC + 3 * nP));
+        BA_CUDA(cudaMemcpyAsync(out, d.dxc, sizeof(T) * 9 * nC, cudaMemcpyDeviceToHost, stream));
+        BA_TRY(fetch_points(d.dxl, 3, out + 9 * nC));
+        break;
+      case BA_BUF_W:
+      case BA_BUF_J: {
+        if ((which == BA_BUF_W) == (opt.compute_kind == BA_IMPLICIT))
+          return fail(BA_ERR_STATE, "BA_BUF_W exists in explicit mode, BA_BUF_J in implicit mode");
+        // the ELL path never materialises Hpl; both buffers are views of the per-observation Jacobian
+        std::vector<T> r(2 * (size_t)g.nE), J(24 * (size_t)g.nE);
+        BA_TRY(eval_edges(r.data(), J.data()));
+        if (which == BA_BUF_J) { memcpy(out, J.data(), sizeof(T) * 24 * g.nE); break; }
+        std::vector<T> h_info;
+        if (d.r_info) {
+          h_info.resize(4 * (size_t)g.nRows * 32);
+          BA_CUDA(cudaMemcpyAsync(h_info.data(), d.r_info, sizeof(T) * h_info.size(), cudaMemcpyDeviceToHost, stream));
+          BA_CUDA(cudaStreamSynchronize(stream));
+        }
+        for (int64_t e = 0; e < g.nE; ++e) {
+          const int slot = g.slot_of_edge[e];
+          const T *Je = J.data() + 24 * e;
+          T om[4] = {T(1), T(0), T(0), T(1)};
+          if (d.r_info && slot >= 0) for (int k = 0; k < 4; ++k) om[k] = h_info[4 * (size_t)slot + k];
+          for (int y = 0; y < 9; ++y) {
+            const T L0 = Je[y] * om[0] + Je[12 + y] * om[2], L1 = Je[y] * om[1] + Je[12 + y] * om[3];
+            for (int q = 0; q < 3; ++q) out[27 * e + 3 * y + q] = slot < 0 ? T(0) : L0 * Je[9 + q] + L1 * Je[21 + q];
+          }
+        }
+        break;
+      }
+      default:
+        return fail(BA_ERR_ARG, "unknown buffer id %d", which);
+    }
+    BA_CUDA(cudaStreamSynchronize(stream));
+    return BA_OK;
+  }
+
   int write_dx(const void *dx_v) override {
     if (!dx_v) return fail(BA_ERR_ARG, "null dx");
     BA_CUDA(cudaSetDevice(opt.device));
     const T *dx = (const T *)dx_v;
     BA_CUDA(cudaMemcpyAsync(d.dxc, dx, sizeof(T) * 9 * g.nC, cudaMemcpyHostToDevice, stream));
-    if (g.nPl)
+    if (g.ell && g.nPl) {
+      BA_CUDA(cudaMemcpyAsync(pt_nat, dx + 9 * g.nC + 3 * g.pt_begin, sizeof(T) * 3 * g.nPl, cudaMemcpyHostToDevice, stream));
+      BA_CUDA(launch_permute3<T>(pt_nat, d.dxl, perm_dev, g.nPl, 1, stream));
+    } else if (g.nPl)
       BA_CUDA(cudaMemcpyAsync(d.dxl, dx + 9 * g.nC + 3 * g.pt_begin, sizeof(T) * 3 * g.nPl, cudaMemcpyHostToDevice, stream));
     BA_CUDA(cudaStreamSynchronize(stream));
     return BA_OK;
@@ -783,11 +1054,11 @@ struct ImplT : Impl {
   int eval_edges(void *r_v, void *J_v) override {
     if (!r_v) return fail(BA_ERR_ARG, "null residual buffer");
     BA_CUDA(cudaSetDevice(opt.device));
-    const size_t nSlots = (size_t)g.nSlabs * TE;
+    const size_t nSlots = g.ell ? (size_t)g.nRows * 32 : (size_t)g.nSlabs * TE;
     T *dr = nullptr, *dJ = nullptr;
     BA_CUDA(cudaMalloc(&dr, sizeof(T) * std::max<size_t>(2 * nSlots, 2)));
     if (J_v) BA_CUDA(cudaMalloc(&dJ, sizeof(T) * std::max<size_t>(24 * nSlots, 24)));
-    cudaError_t e = launch_eval_edges<T>(d, dr, dJ, stream);
+    cudaError_t e = g.ell ? launch_eval_edges_ell<T>(d, dr, dJ, stream) : launch_eval_edges<T>(d, dr, dJ, stream);
     stats.launches += 1;
     std::vector<T> hr(2 * nSlots), hJ(J_v ? 24 * nSlots : 0);
     if (e == cudaSuccess && nSlots) e = cudaMemcpyAsync(hr.data(), dr, sizeof(T) * 2 * nSlots, cudaMemcpyDeviceToHost, stream);
@@ -809,11 +1080,10 @@ struct ImplT : Impl {
     if (!p_v || !q_v) return fail(BA_ERR_ARG, "null vector");
     if (!linearized) return fail(BA_ERR_STATE, "ba_schur_apply before ba_linearize");
     BA_CUDA(cudaSetDevice(opt.device));
-    BA_CUDA(launch_prep<T>(d, stream));
-    stats.launches += launches_of_prep();
+    BA_TRY(prep());
     BA_CUDA(cudaMemsetAsync(d.sB, 0, sizeof(T) * NREP * 9 * g.nC, stream));
     BA_CUDA(cudaMemcpyAsync(d.z, p_v, sizeof(T) * 9 * g.nC, cudaMemcpyHostToDevice, stream));
-    BA_CUDA(launch_pad_cam<T>(d, d.z, stream));
+    BA_TRY(pad_cam(d.z));
     BA_TRY(schur_edge(SM_FULL, d.xpad, d.sB, 0, true));
     BA_CUDA(launch_fold_replicas<T>(d, d.sB, 1, stream));
     BA_TRY(allreduce_T(d.sB, 9 * (size_t)g.nC));
@@ -843,6 +1113,15 @@ struct ImplT : Impl {
   // A_lin = nE(8+29s) + nP 15 s + nC 99 s  (26s implicit).  Per rank: local nE, nP.
   int algorithmic_bytes(double *a, double *b) override {
     const double s = sizeof(T), nE = g.nEl, nP = g.nPl, nC = g.nC;
+    if (g.ell) {
+      // ELL: per observation the operator stream (K scalars) + its camera index; per point Hll^-1 (9) and,
+      // for the factored stream, X (3); the camera term as in the tile layout.  Linearisation: camera index + two
+      // copies of the observation (point- and camera-major) + point index in, stream out.
+      const double kw = d.store == ST_FACT ? 8. : 24.;
+      if (a) *a = nE * (kw * s + 4.) + nP * ((d.store == ST_FACT ? 12. : 9.) * s) + nC * 216. * s;
+      if (b) *b = nE * (8. + (kw + 4.) * s) + nP * 15. * s + nC * 99. * s;
+      return BA_OK;
+    }
     const double kw = d.implicit ? 24. : 27.;
     if (a) *a = nE * (kw * s + 4.) + nP * (9. * s + 4.) + nC * 216. * s;
     if (b) *b = nE * (8. + (kw + 2.) * s) + nP * 15. * s + nC * 99. * s;
@@ -898,6 +1177,36 @@ int ba_layout(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const i
   return BA_OK;
 }
 
+int ba_layout_ell(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx, const int32_t *pt_idx,
+                  ba_ell_sizes *sizes, int32_t *warp, int32_t *perm, int64_t *edge_of_slot, int32_t *slot_cam,
+                  int32_t *chunk, int32_t *cm_slot) {
+  if (!opt || (nE > 0 && (!cam_idx || !pt_idx))) return BA_ERR_ARG;
+  if (opt->world_size < 1 || opt->rank < 0 || opt->rank >= opt->world_size) return BA_ERR_ARG;
+  ba::HostGraph g;
+  g.ell = true;
+  std::string err;
+  const int rc = ba::build_host_graph(*opt, nC, nP, nE, cam_idx, pt_idx, g, err);
+  if (rc != BA_OK) return rc;
+  const size_t nSlots = (size_t)g.nRows * 32;
+  if (sizes) {
+    sizes->n_warps = g.nW; sizes->n_rows = g.nRows; sizes->n_slots = (int64_t)nSlots; sizes->n_local_edges = g.nEl;
+    sizes->n_local_points = g.nPl; sizes->n_chunks = g.nChunks; sizes->pt_begin = g.pt_begin; sizes->n_heavy = g.nHeavy;
+  }
+  for (int w = 0; warp && w < g.nW; ++w) {
+    warp[4 * w] = g.wdesc[w].x; warp[4 * w + 1] = g.wdesc[w].y; warp[4 * w + 2] = g.wdesc[w].z; warp[4 * w + 3] = g.wdesc[w].w;
+  }
+  for (int p = 0; perm && p < g.nPl; ++p) perm[p] = g.perm[p];
+  for (size_t i = 0; i < nSlots; ++i) {
+    if (edge_of_slot) edge_of_slot[i] = g.edge_of_slot[i];
+    if (slot_cam) slot_cam[i] = g.e_cam[i];
+  }
+  for (int k = 0; chunk && k < g.nChunks; ++k) {
+    chunk[4 * k] = g.chunk[k].x; chunk[4 * k + 1] = g.chunk[k].y; chunk[4 * k + 2] = g.chunk[k].z; chunk[4 * k + 3] = g.chunk[k].w;
+  }
+  for (int k = 0; cm_slot && k < g.nEl; ++k) cm_slot[k] = g.cm_slot[k];
+  return BA_OK;
+}
+
 int ba_create(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx,
               const int32_t *pt_idx, const void *obs, ba_solver **out) {
   if (!opt || !out || (nE > 0 && (!cam_idx || !pt_idx || !obs))) return BA_ERR_ARG;
@@ -916,6 +1225,13 @@ int ba_create(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const i
   if (opt->dtype == BA_F64) impl.reset(new ba::ImplT<double>());
   else impl.reset(new ba::ImplT<float>());
   impl->opt = *opt;
+  {
+    int layout = 0, store = 0;
+    int rcfg = ba::resolve_layout(*opt, &layout, &store);
+    if (rcfg != BA_OK) { g_create_error = "unsupported layout / operator_store combination"; return rcfg; }
+    impl->g.ell = layout == BA_LAYOUT_ELL;
+    impl->store_cfg = store;
+  }
   int rc = ba::build_host_graph(*opt, nC, nP, nE, cam_idx, pt_idx, impl->g, impl->err);
   if (rc != BA_OK) { g_create_error = impl->err; return rc; }
   rc = impl->init(obs);

@@ -1,0 +1,657 @@
+// ba_ell.cu -- sm_100a kernels of the ELL layout (thread per point, warp per slice; see ba_internal.h).
+//
+// Reference functions replaced (the same ones as ba_kernels.cu, different data layout):
+//   k_cam_consts    per-camera rotation constants and the transform blocks of the factored operator; the
+//                   reference recomputes sin/cos per OBSERVATION (src/geo/analytical_derivatives.cu:16-159).
+//   k_lin_ell       <- AnalyticalDerivativesKernelGradKernel (analytical_derivatives.cu:162-285) fused with the
+//                   point side of makeHSchur / makeHSchurWithInfo / makeHppHllSchur
+//                   (src/edge/build_linear_system.cu:88-239, build_implicit_linear_system.cu:65-111) and
+//                   computeResidualNorm (src/algo/lm_algo.cu:26-51): Hll, g_l and the operator stream; each
+//                   thread owns one point, so Hll / g_l are plain register sums (no atomics, no shared memory).
+//   k_schur_ell     <- one operator application of the PCG loop: the two cusparseSpMV calls + the batched
+//                   Hll^-1 product (src/solver/schur_pcg_solver.cu:315-357), MakeV (:430-510), SolveW (:513-596)
+//                   and the matrix-free implicitETMulx / implicitEMulx (implicit_schur_pcg_solver.cu:21-90).
+//   k_trial_ell     <- updateDeltaXTwoVertices + forward + JdxpF + reductions (src/edge/update.cu:14-41,
+//                   src/algo/lm_algo.cu:61-126).
+//   k_prep_points_ell <- processDiag + the 3x3 cublasXmatinvBatched + w = Hll^-1 g_l
+//                   (schur_LM_linear_system.cu:114-185, schur_pcg_solver.cu:61-97,467-476).
+#include <math.h>
+#include <stdlib.h>
+
+#include "ba_device_utils.cuh"
+#include "ba_geometry.cuh"
+#include "ba_internal.h"
+
+namespace ba {
+
+constexpr int ELL_THREADS = ELL_WARPS * 32;
+
+struct WDesc { int row0, D, pt0, heavy, np; };
+__device__ __forceinline__ WDesc load_desc(const int4 *wdesc, int w) {
+  const int4 v = __ldg(wdesc + w);
+  return WDesc{v.x, v.y, v.z, v.w & 0xff, v.w >> 8};
+}
+
+// one camera's constants (CAMC scalars, 16-byte aligned rows) with 16-byte loads
+template <typename T>
+__device__ __forceinline__ void load_camc(const T *__restrict__ camc, int c, T *cm, RotConst<T> &rc) {
+  using V = typename CamPad<T>::vec;
+  constexpr int NV = CAMC * sizeof(T) / 16;
+  __align__(16) T v[CAMC];
+  const V *src = reinterpret_cast<const V *>(camc + (size_t)CAMC * c);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) reinterpret_cast<V *>(v)[k] = __ldg(src + k);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cm[k] = v[k];
+  rc.c = v[9]; rc.a = v[10]; rc.b = v[11]; rc.ap = v[12]; rc.bp = v[13];
+  rc.small = v[14] != T(0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_cam_consts(Dev<T> d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.nC) return;
+  T cm[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cm[k] = d.cam[9 * (size_t)c + k];
+  const RotConst<T> rc = rot_const<T>(cm[0], cm[1], cm[2]);
+  T *o = d.camc + (size_t)CAMC * c;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) o[k] = cm[k];
+  o[9] = rc.c; o[10] = rc.a; o[11] = rc.b; o[12] = rc.ap; o[13] = rc.bp;
+  o[14] = rc.small ? T(1) : T(0);
+  o[15] = T(0);
+  T tr[CAMT];
+  camera_transform<T>(cm, rc, tr);
+#pragma unroll
+  for (int k = 0; k < CAMT; ++k) d.camT[(size_t)CAMT * c + k] = tr[k];
+  if (rc.small) d.scal[S_ANY_SMALL] = 1.;  // the factored stream is not used while any camera is in the Taylor branch
+}
+
+// operator stream, row-blocked: pair j of slot (row, lane)
+template <typename T, int K>
+__device__ __forceinline__ void load_stream(const T *__restrict__ WJ, size_t row, int lane, T *v) {
+  using V = typename Vec2<T>::type;
+  const V *src = reinterpret_cast<const V *>(WJ) + row * (size_t)(K / 2 * 32) + lane;
+#pragma unroll
+  for (int j = 0; j < K / 2; ++j) {
+    const V x = __ldg(src + j * 32);
+    v[2 * j] = x.x;
+    v[2 * j + 1] = x.y;
+  }
+}
+template <typename T, int K>
+__device__ __forceinline__ void store_stream(T *WJ, size_t row, int lane, const T *v) {
+  using V = typename Vec2<T>::type;
+  V *dst = reinterpret_cast<V *>(WJ) + row * (size_t)(K / 2 * 32) + lane;
+#pragma unroll
+  for (int j = 0; j < K / 2; ++j) {
+    V x;
+    x.x = v[2 * j];
+    x.y = v[2 * j + 1];
+    dst[j * 32] = x;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void load_info(const T *__restrict__ r_info, size_t slot, T *om) {
+  using V = typename Vec2<T>::type;
+  const V a = __ldg(reinterpret_cast<const V *>(r_info) + 2 * slot), b = __ldg(reinterpret_cast<const V *>(r_info) + 2 * slot + 1);
+  om[0] = a.x; om[1] = a.y; om[2] = b.x; om[3] = b.y;
+}
+
+// --------------------------------------------------------------------------------
+// HP1, point side.  DISPATCH: 0 run; 1 run unless a camera is in the small-angle branch; 2 run only then
+// (the flag is produced on the device by k_cam_consts just before, so the host launches both flavours of a
+// factored-store solver back to back and exactly one of them does the work).
+template <typename T, int STORE, bool INFO>
+__global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch) {
+  constexpr int K = STORE == ST_FACT ? 8 : 24;
+  if (dispatch) {
+    const bool any_small = d.scal[S_ANY_SMALL] != 0.;
+    if (any_small != (dispatch == 2)) return;
+  }
+  const int lane = threadIdx.x & 31, w = blockIdx.x * ELL_WARPS + (threadIdx.x >> 5);
+  if (w >= d.nW) return;
+  const WDesc wd = load_desc(d.wdesc, w);
+  const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
+  const bool pvalid = wd.heavy || lane < wd.np;
+  T X0 = T(0), X1 = T(0), X2 = T(0);
+  if (pvalid) { X0 = d.pt[3 * (size_t)p]; X1 = d.pt[3 * (size_t)p + 1]; X2 = d.pt[3 * (size_t)p + 2]; }
+  T hl[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) hl[k] = T(0);
+  double cost = 0.;
+  for (int r = 0; r < wd.D; ++r) {
+    const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    if (c < 0) continue;
+    T cm[9];
+    RotConst<T> rc;
+    load_camc<T>(d.camc, c, cm, rc);
+    const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
+    T r0, r1, Jp[6];
+    if (STORE == ST_FACT) {
+      T sv[8];
+      edge_point_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, sv, sv[6], sv[7]);
+      store_stream<T, K>(d.WJ, row, lane, sv);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Jp[k] = sv[k];
+    } else {
+      T J[24];
+      edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+      store_stream<T, K>(d.WJ, row, lane, J);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { Jp[q] = J[9 + q]; Jp[3 + q] = J[21 + q]; }
+    }
+    cost += (double)(r0 * r0) + (double)(r1 * r1);
+    T L[6];  // Omega-weighted rows of Jp (JMulInfo, build_linear_system.cu:149-176); identity without information
+    if (INFO) {
+      T om[4];
+      load_info<T>(d.r_info, slot, om);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        L[q] = Jp[q] * om[0] + Jp[3 + q] * om[2];
+        L[3 + q] = Jp[q] * om[1] + Jp[3 + q] * om[3];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) L[q] = Jp[q];
+    }
+#pragma unroll
+    for (int y = 0; y < 3; ++y) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) hl[3 * y + q] += L[y] * Jp[q] + L[3 + y] * Jp[3 + q];
+      hl[9 + y] -= L[y] * r0 + L[3 + y] * r1;
+    }
+  }
+  if (wd.heavy) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) hl[k] = warp_sum<T>(hl[k]);
+  }
+  if (pvalid && (!wd.heavy || lane == 0)) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) d.Hll[9 * (size_t)p + k] = hl[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d.gl[3 * (size_t)p + k] = hl[9 + k];
+  }
+  cost = warp_sum<double>(cost);
+  if (lane == 0) d.partials[w] = cost;
+}
+
+// --------------------------------------------------------------------------------
+// Solve preparation, point side: damped 3x3 inverse, w = Hll^-1 g_l, and the plane copies the edge kernel reads.
+template <typename T>
+__global__ void __launch_bounds__(256) k_prep_points_ell(Dev<T> d) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.nPl) return;
+  const T a1 = T(d.damp) + T(1);  // (a + 1) * diag, schur_LM_linear_system.cu:123-124,149
+  T h[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) h[k] = d.Hll[9 * (size_t)p + k];
+  h[0] *= a1; h[4] *= a1; h[8] *= a1;
+  const T c00 = h[4] * h[8] - h[5] * h[7], c01 = h[5] * h[6] - h[3] * h[8], c02 = h[3] * h[7] - h[4] * h[6];
+  const T det = h[0] * c00 + h[1] * c01 + h[2] * c02;
+  const T id = det != T(0) ? T(1) / det : T(0);
+  T inv[9];
+  inv[0] = c00 * id;
+  inv[1] = (h[2] * h[7] - h[1] * h[8]) * id;
+  inv[2] = (h[1] * h[5] - h[2] * h[4]) * id;
+  inv[3] = c01 * id;
+  inv[4] = (h[0] * h[8] - h[2] * h[6]) * id;
+  inv[5] = (h[2] * h[3] - h[0] * h[5]) * id;
+  inv[6] = c02 * id;
+  inv[7] = (h[1] * h[6] - h[0] * h[7]) * id;
+  inv[8] = (h[0] * h[4] - h[1] * h[3]) * id;
+  const size_t np = (size_t)d.nPlPad;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) d.HllInvP[k * np + p] = inv[k];
+  const T g0 = d.gl[3 * (size_t)p], g1 = d.gl[3 * (size_t)p + 1], g2 = d.gl[3 * (size_t)p + 2];
+#pragma unroll
+  for (int y = 0; y < 3; ++y) {
+    d.wP[y * np + p] = inv[3 * y] * g0 + inv[3 * y + 1] * g1 + inv[3 * y + 2] * g2;
+    d.XP[y * np + p] = d.pt[3 * (size_t)p + y];
+  }
+}
+
+// --------------------------------------------------------------------------------
+// Per-observation halves of the operator.
+//   first half:  t += W^T x   second half: o = W u   (W = Jc^T Omega Jp, never formed)
+// ST_FACT: s = {Jp[6], B[2]}, g = T_c x = (psi, xt, e); the second half produces o = (X x v, v, (B.z)(1,l2,l2^2)),
+// to which the camera kernel applies T_c^T.
+template <typename T, bool INFO>
+__device__ __forceinline__ void fact_first(const T *s, const T *g, T X0, T X1, T X2, const T *om, T &t0, T &t1, T &t2) {
+  const T q0 = g[1] * X2 - g[2] * X1 + g[3];
+  const T q1 = g[2] * X0 - g[0] * X2 + g[4];
+  const T q2 = g[0] * X1 - g[1] * X0 + g[5];
+  const T l2 = s[6] * s[6] + s[7] * s[7];
+  const T poly = g[6] + l2 * (g[7] + l2 * g[8]);
+  T y0 = s[0] * q0 + s[1] * q1 + s[2] * q2 + s[6] * poly;
+  T y1 = s[3] * q0 + s[4] * q1 + s[5] * q2 + s[7] * poly;
+  if (INFO) {  // t = Jp^T Omega^T (Jc x)
+    const T a = om[0] * y0 + om[2] * y1, b = om[1] * y0 + om[3] * y1;
+    y0 = a; y1 = b;
+  }
+  t0 += s[0] * y0 + s[3] * y1;
+  t1 += s[1] * y0 + s[4] * y1;
+  t2 += s[2] * y0 + s[5] * y1;
+}
+template <typename T, bool INFO>
+__device__ __forceinline__ void fact_second(const T *s, T u0, T u1, T u2, T X0, T X1, T X2, const T *om, T *o) {
+  T z0 = s[0] * u0 + s[1] * u1 + s[2] * u2, z1 = s[3] * u0 + s[4] * u1 + s[5] * u2;
+  if (INFO) {  // s = Jc^T Omega (Jp u)
+    const T a = om[0] * z0 + om[1] * z1, b = om[2] * z0 + om[3] * z1;
+    z0 = a; z1 = b;
+  }
+  const T v0 = s[0] * z0 + s[3] * z1, v1 = s[1] * z0 + s[4] * z1, v2 = s[2] * z0 + s[5] * z1;
+  o[0] = X1 * v2 - X2 * v1;
+  o[1] = X2 * v0 - X0 * v2;
+  o[2] = X0 * v1 - X1 * v0;
+  o[3] = v0; o[4] = v1; o[5] = v2;
+  const T l2 = s[6] * s[6] + s[7] * s[7];
+  const T bz = s[6] * z0 + s[7] * z1;
+  o[6] = bz; o[7] = bz * l2; o[8] = bz * l2 * l2;
+}
+// ST_J: s = J[2][12], g = x (the plain camera vector)
+template <typename T, bool INFO>
+__device__ __forceinline__ void jac_first(const T *J, const T *x, const T *om, T &t0, T &t1, T &t2) {
+  T a0 = T(0), a1 = T(0);
+#pragma unroll
+  for (int y = 0; y < 9; ++y) { a0 += J[y] * x[y]; a1 += J[12 + y] * x[y]; }
+  if (INFO) {
+    const T a = om[0] * a0 + om[2] * a1, b = om[1] * a0 + om[3] * a1;
+    a0 = a; a1 = b;
+  }
+  t0 += J[9] * a0 + J[21] * a1;
+  t1 += J[10] * a0 + J[22] * a1;
+  t2 += J[11] * a0 + J[23] * a1;
+}
+template <typename T, bool INFO>
+__device__ __forceinline__ void jac_second(const T *J, T u0, T u1, T u2, const T *om, T *o) {
+  T b0 = J[9] * u0 + J[10] * u1 + J[11] * u2, b1 = J[21] * u0 + J[22] * u1 + J[23] * u2;
+  if (INFO) {
+    const T a = om[0] * b0 + om[1] * b1, b = om[2] * b0 + om[3] * b1;
+    b0 = a; b1 = b;
+  }
+#pragma unroll
+  for (int y = 0; y < 9; ++y) o[y] = J[y] * b0 + J[12 + y] * b1;
+}
+
+template <typename T>
+__host__ __device__ constexpr size_t schur_ell_smem() {
+  return (size_t)ELL_WARPS * 32 * 9 * sizeof(T) + (size_t)ELL_WARPS * 32 * sizeof(int);
+}
+
+// HP2 edge kernel of the ELL layout.  One warp per slice (lane = point) or per heavy point (lane = observation).
+//   phase 1: t_j = sum_e W_e^T x[cam(e)]     thread-local (slice) or one warp sum (heavy point)
+//   u_j = Hll^-1 t_j | Hll^-1 t_j - w_j | (BACKSUB: dx_l = w_j - Hll^-1 t_j)
+//   phase 2: s[cam(e)] += W_e u_j            RED.ADD, staged per warp so that one RED covers consecutive components
+// RC rows of the factored stream are kept in registers between the phases; further rows (and the wider Jacobian
+// stream) are read again in phase 2 (an L2 hit: the slice was streamed microseconds earlier).
+template <typename T, int STORE, int MODE, bool INFO, int RC>
+__global__ void __launch_bounds__(ELL_THREADS, RC >= 4 ? 1 : 2)
+k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
+  constexpr int K = STORE == ST_FACT ? 8 : 24;
+  constexpr int NC = RC > 0 ? RC : 1;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sv = reinterpret_cast<T *>(smem_raw);
+  int *sc = reinterpret_cast<int *>(sv + ELL_WARPS * 32 * 9);
+  const int tid = threadIdx.x, lane = tid & 31, w = blockIdx.x * ELL_WARPS + (tid >> 5);
+  const bool wvalid = w < d.nW;
+  WDesc wd{0, 0, 0, 0, 0};
+  if (wvalid) wd = load_desc(d.wdesc, w);
+  const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
+  const bool pvalid = wvalid && (wd.heavy || lane < wd.np);
+  const size_t npl = (size_t)d.nPlPad;
+  // ---- everything up to dependent_ready touches solve-constant data only (overlaps the preceding camera kernel)
+  T X0 = T(0), X1 = T(0), X2 = T(0);
+  if (STORE == ST_FACT && pvalid) { X0 = __ldg(d.XP + p); X1 = __ldg(d.XP + npl + p); X2 = __ldg(d.XP + 2 * npl + p); }
+  T cs[NC][8];
+  int cc[NC];
+  if (RC > 0) {
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      cc[r] = -1;
+      if (r < wd.D) {
+        const size_t row = (size_t)wd.row0 + r;
+        cc[r] = __ldg(d.r_cam + row * 32 + lane);
+        load_stream<T, 8>(d.WJ, row, lane, cs[r]);
+      }
+    }
+  }
+  T hi[9], wv[3] = {T(0), T(0), T(0)};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) hi[k] = T(0);
+  if (pvalid) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInvP + k * npl + p);
+    if (MODE != SM_FULL) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wv[k] = __ldg(d.wP + k * npl + p);
+    }
+  }
+  if (check_active) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the preceding camera kernel (p, state, replica sets) is complete
+    if (!d.st->active) return;
+  }
+  if (MODE == SM_FULL && zero_set) {  // clear the replica set the NEXT edge pass will accumulate into
+    const unsigned tot = (unsigned)NREP * 9u * (unsigned)d.nC;
+    for (unsigned i = blockIdx.x * ELL_THREADS + tid; i < tot; i += gridDim.x * ELL_THREADS) zero_set[i] = T(0);
+  }
+  if (!wvalid) return;  // whole warps only
+  T *dst = MODE != SM_BACKSUB ? sout + (size_t)(blockIdx.x % NREP) * (9 * (size_t)d.nC) : nullptr;
+  // ---- phase 1
+  T t0 = T(0), t1 = T(0), t2 = T(0);
+  auto first = [&](const T *s, int c, size_t slot) {
+    __align__(16) T g[CamPad<T>::N];
+    gather_cam<T, true>(xin, c, g);
+    T om[4];
+    if (INFO) load_info<T>(d.r_info, slot, om);
+    if (STORE == ST_FACT) fact_first<T, INFO>(s, g, X0, X1, X2, om, t0, t1, t2);
+    else jac_first<T, INFO>(s, g, om, t0, t1, t2);
+  };
+  if (RC > 0) {
+#pragma unroll
+    for (int r = 0; r < NC; ++r)
+      if (r < wd.D && cc[r] >= 0) first(cs[r], cc[r], ((size_t)wd.row0 + r) * 32 + lane);
+  }
+#pragma unroll 2
+  for (int r = RC; r < wd.D; ++r) {
+    const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    T s[K];
+    load_stream<T, K>(d.WJ, row, lane, s);
+    if (c >= 0) first(s, c, slot);
+  }
+  if (wd.heavy) { t0 = warp_sum<T>(t0); t1 = warp_sum<T>(t1); t2 = warp_sum<T>(t2); }
+  // ---- point step
+  T u0 = hi[0] * t0 + hi[1] * t1 + hi[2] * t2;
+  T u1 = hi[3] * t0 + hi[4] * t1 + hi[5] * t2;
+  T u2 = hi[6] * t0 + hi[7] * t1 + hi[8] * t2;
+  if (MODE == SM_INIT) { u0 -= wv[0]; u1 -= wv[1]; u2 -= wv[2]; }  // u = Hll^-1 Hlp x0 - w: one pass yields Hpl Hll^-1 Hlp x0 - Hpl w
+  if (MODE == SM_BACKSUB) {
+    if (pvalid && (!wd.heavy || lane == 0)) {
+      d.dxl[3 * (size_t)p] = wv[0] - u0;
+      d.dxl[3 * (size_t)p + 1] = wv[1] - u1;
+      d.dxl[3 * (size_t)p + 2] = wv[2] - u2;
+    }
+    return;
+  }
+  // ---- phase 2
+  auto second = [&](const T *s, int c, size_t slot) {
+    T o[9];
+    if (c >= 0) {
+      T om[4];
+      if (INFO) load_info<T>(d.r_info, slot, om);
+      if (STORE == ST_FACT) fact_second<T, INFO>(s, u0, u1, u2, X0, X1, X2, om, o);
+      else jac_second<T, INFO>(s, u0, u1, u2, om, o);
+    }
+    warp_scatter9<T>(sv, sc, o, c, dst);
+  };
+  if (RC > 0) {
+#pragma unroll
+    for (int r = 0; r < NC; ++r)
+      if (r < wd.D) second(cs[r], cc[r], ((size_t)wd.row0 + r) * 32 + lane);
+  }
+  for (int r = RC; r < wd.D; ++r) {
+    const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    T s[K];
+    load_stream<T, K>(d.WJ, row, lane, s);
+    second(s, c, slot);
+  }
+}
+
+// --------------------------------------------------------------------------------
+// LM scalars: sum (J dx + r)^2 at x and sum r^2 at x + dx in one pass.
+template <typename T>
+__global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
+  const int lane = threadIdx.x & 31, w = blockIdx.x * ELL_WARPS + (threadIdx.x >> 5);
+  if (w >= d.nW) return;
+  const WDesc wd = load_desc(d.wdesc, w);
+  const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
+  const bool pvalid = wd.heavy || lane < wd.np;
+  T X0 = T(0), X1 = T(0), X2 = T(0), D0 = T(0), D1 = T(0), D2 = T(0);
+  if (pvalid) {
+    X0 = d.pt[3 * (size_t)p]; X1 = d.pt[3 * (size_t)p + 1]; X2 = d.pt[3 * (size_t)p + 2];
+    D0 = d.dxl[3 * (size_t)p]; D1 = d.dxl[3 * (size_t)p + 1]; D2 = d.dxl[3 * (size_t)p + 2];
+  }
+  double a_model = 0., a_cost = 0.;
+  for (int r = 0; r < wd.D; ++r) {
+    const size_t slot = ((size_t)wd.row0 + r) * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    if (c < 0) continue;
+    T cm[9], dc[9];
+    RotConst<T> rc;
+    load_camc<T>(d.camc, c, cm, rc);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dc[k] = d.dxc[9 * (size_t)c + k];
+    const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
+    T J[24], r0, r1;
+    edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    T m0 = T(0), m1 = T(0);  // J dx  (JdxpF, lm_algo.cu:61-79)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { m0 += J[k] * dc[k]; m1 += J[12 + k] * dc[k]; }
+    m0 += J[9] * D0 + J[10] * D1 + J[11] * D2;
+    m1 += J[21] * D0 + J[22] * D1 + J[23] * D2;
+    a_model += (double)((m0 + r0) * (m0 + r0)) + (double)((m1 + r1) * (m1 + r1));
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cm[k] += dc[k];  // updateDeltaXTwoVertices, update.cu:14-41
+    rc = rot_const<T>(cm[0], cm[1], cm[2]);
+    T s0, s1;
+    edge_residual<T>(cm, rc, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1);
+    a_cost += (double)(s0 * s0) + (double)(s1 * s1);
+  }
+  a_cost = warp_sum<double>(a_cost);
+  a_model = warp_sum<double>(a_model);
+  if (lane == 0) {
+    d.partials[2 * (size_t)w] = a_cost;
+    d.partials[2 * (size_t)w + 1] = a_model;
+  }
+}
+
+// debug / parity: r[slot][2], J[slot][24]
+template <typename T>
+__global__ void __launch_bounds__(ELL_THREADS) k_eval_edges_ell(Dev<T> d, T *r_out, T *J_out) {
+  const int lane = threadIdx.x & 31, w = blockIdx.x * ELL_WARPS + (threadIdx.x >> 5);
+  if (w >= d.nW) return;
+  const WDesc wd = load_desc(d.wdesc, w);
+  const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
+  const bool pvalid = wd.heavy || lane < wd.np;
+  T X0 = T(0), X1 = T(0), X2 = T(0);
+  if (pvalid) { X0 = d.pt[3 * (size_t)p]; X1 = d.pt[3 * (size_t)p + 1]; X2 = d.pt[3 * (size_t)p + 2]; }
+  for (int r = 0; r < wd.D; ++r) {
+    const size_t slot = ((size_t)wd.row0 + r) * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    if (c < 0) continue;
+    T cm[9];
+    RotConst<T> rc;
+    load_camc<T>(d.camc, c, cm, rc);
+    const T o0 = d.r_obs[2 * slot], o1 = d.r_obs[2 * slot + 1];
+    T J[24], r0, r1;
+    edge_residual_jacobian<T>(cm, rc, X0, X1, X2, o0, o1, r0, r1, J);
+    r_out[2 * slot] = r0;
+    r_out[2 * slot + 1] = r1;
+    if (J_out) {
+#pragma unroll
+      for (int k = 0; k < 24; ++k) J_out[24 * slot + k] = J[k];
+    }
+  }
+}
+
+// xpad = T_c x (the vector the factored edge pass gathers)
+template <typename T>
+__global__ void __launch_bounds__(256) k_pad_cam_T(const T *__restrict__ src, const T *__restrict__ camT, T *dst, int nC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * nC) return;
+  const int c = i / 9, k = i - 9 * c, bk = k / 3, kk = k - 3 * bk;
+  const T *tb = camT + (size_t)CAMT * c + 9 * bk;
+  const T *x = src + 9 * (size_t)c + 3 * bk;
+  // block 1 of T_c is R^T (stored: R)
+  const T v = bk == 1 ? tb[kk] * x[0] + tb[3 + kk] * x[1] + tb[6 + kk] * x[2]
+                      : tb[3 * kk] * x[0] + tb[3 * kk + 1] * x[1] + tb[3 * kk + 2] * x[2];
+  dst[(size_t)CamPad<T>::N * c + k] = v;
+}
+
+// dst[i] = src[perm[i]] (gather != 0) or dst[perm[i]] = src[i], three scalars per entry
+template <typename T>
+__global__ void __launch_bounds__(256) k_permute3(const T *__restrict__ src, T *dst, const int *__restrict__ perm, int n, int gather) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = perm[i];
+  const size_t a = gather ? (size_t)j : (size_t)i, b = gather ? (size_t)i : (size_t)j;
+  dst[3 * b] = src[3 * a];
+  dst[3 * b + 1] = src[3 * a + 1];
+  dst[3 * b + 2] = src[3 * a + 2];
+}
+
+// --------------------------------------------------------------------------------
+// launchers
+static int ell_grid(int nW) { return (nW + ELL_WARPS - 1) / ELL_WARPS; }
+
+template <typename T>
+cudaError_t launch_cam_consts(const Dev<T> &d, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(d.scal + S_ANY_SMALL, 0, sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  k_cam_consts<T><<<(d.nC + 127) / 128, 128, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+template <typename T, int STORE>
+static void launch_lin_ell_s(const Dev<T> &d, int dispatch, cudaStream_t st) {
+  if (d.r_info) k_lin_ell<T, STORE, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, dispatch);
+  else k_lin_ell<T, STORE, false><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, dispatch);
+}
+
+// d.store is the CONFIGURED store here: ST_FACT launches both point-side flavours (device-side dispatch on the
+// small-angle flag written by k_cam_consts), ST_J only the Jacobian flavour.
+template <typename T>
+cudaError_t launch_linearize_ell(const Dev<T> &d, cudaStream_t st) {
+  if (d.nW > 0) {
+    if (d.store == ST_FACT) {
+      launch_lin_ell_s<T, ST_FACT>(d, 1, st);
+      launch_lin_ell_s<T, ST_J>(d, 2, st);
+    } else {
+      launch_lin_ell_s<T, ST_J>(d, 0, st);
+    }
+  }
+  cudaError_t e = launch_lin_cm<T>(d, st);
+  if (e != cudaSuccess) return e;
+  k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nW, 1, d.scal + S_COST);
+  return cudaGetLastError();
+}
+int launches_of_linearize_ell() { return 5; }
+
+int ell_rc() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("BA_ELL_RC"); v = e ? atoi(e) : 2; }
+  return v;
+}
+
+template <typename T, int STORE, int MODE, bool INFO, int RC>
+static cudaError_t launch_schur_ell_v(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  auto kern = k_schur_ell<T, STORE, MODE, INFO, RC>;
+  constexpr size_t smem = schur_ell_smem<T>();
+  const int grid = ell_grid(d.nW);
+  if (check_active && pdl_enabled()) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(ELL_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, d, xin, sout, zero_set, check_active);
+  }
+  kern<<<grid, ELL_THREADS, smem, st>>>(d, xin, sout, zero_set, check_active);
+  return cudaGetLastError();
+}
+
+template <typename T, int STORE, int MODE, bool INFO>
+static cudaError_t launch_schur_ell_rc(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  if constexpr (STORE != ST_FACT) {
+    return launch_schur_ell_v<T, STORE, MODE, INFO, 0>(d, xin, sout, zero_set, check_active, st);
+  } else if constexpr (INFO || MODE != SM_FULL) {
+    return launch_schur_ell_v<T, STORE, MODE, INFO, 2>(d, xin, sout, zero_set, check_active, st);
+  } else {
+    switch (ell_rc()) {  // the hot flavour: how many rows stay in registers between the phases is a tuning knob (BA_ELL_RC)
+      case 0: return launch_schur_ell_v<T, STORE, MODE, INFO, 0>(d, xin, sout, zero_set, check_active, st);
+      case 4: return launch_schur_ell_v<T, STORE, MODE, INFO, 4>(d, xin, sout, zero_set, check_active, st);
+      case 6: return launch_schur_ell_v<T, STORE, MODE, INFO, 6>(d, xin, sout, zero_set, check_active, st);
+      default: return launch_schur_ell_v<T, STORE, MODE, INFO, 2>(d, xin, sout, zero_set, check_active, st);
+    }
+  }
+}
+
+template <typename T, int STORE, int MODE>
+static cudaError_t launch_schur_ell_i(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  if (d.r_info) return launch_schur_ell_rc<T, STORE, MODE, true>(d, xin, sout, zero_set, check_active, st);
+  return launch_schur_ell_rc<T, STORE, MODE, false>(d, xin, sout, zero_set, check_active, st);
+}
+
+template <typename T, int STORE>
+static cudaError_t launch_schur_ell_m(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  switch (mode) {
+    case SM_FULL: return launch_schur_ell_i<T, STORE, SM_FULL>(d, xin, sout, zero_set, check_active, st);
+    case SM_INIT: return launch_schur_ell_i<T, STORE, SM_INIT>(d, xin, sout, zero_set, check_active, st);
+    case SM_BACKSUB: return launch_schur_ell_i<T, STORE, SM_BACKSUB>(d, xin, sout, zero_set, check_active, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// d.store is the EFFECTIVE store of the current linearisation (ST_FACT or ST_J)
+template <typename T>
+cudaError_t launch_schur_ell(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  if (d.nW == 0) return cudaSuccess;
+  if (d.store == ST_FACT) return launch_schur_ell_m<T, ST_FACT>(d, mode, xin, sout, zero_set, check_active, st);
+  return launch_schur_ell_m<T, ST_J>(d, mode, xin, sout, zero_set, check_active, st);
+}
+
+template <typename T>
+cudaError_t launch_prep_ell(const Dev<T> &d, cudaStream_t st) {
+  if (d.nPl > 0) k_prep_points_ell<T><<<(d.nPl + 255) / 256, 256, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st) {
+  if (d.nW > 0) k_trial_ell<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+  k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nW, 2, d.scal + S_TRIAL_COST);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_eval_edges_ell(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st) {
+  if (d.nW > 0) k_eval_edges_ell<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, r_slots, J_slots);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_pad_cam_T(const Dev<T> &d, const T *src, cudaStream_t st) {
+  k_pad_cam_T<T><<<(9 * d.nC + 255) / 256, 256, 0, st>>>(src, d.camT, d.xpad, d.nC);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_permute3(const T *src, T *dst, const int *perm, int n, int gather, cudaStream_t st) {
+  if (n > 0) k_permute3<T><<<(n + 255) / 256, 256, 0, st>>>(src, dst, perm, n, gather);
+  return cudaGetLastError();
+}
+
+#define BA_INSTANTIATE_ELL(T)                                                                                 \
+  template cudaError_t launch_cam_consts<T>(const Dev<T> &, cudaStream_t);                                    \
+  template cudaError_t launch_linearize_ell<T>(const Dev<T> &, cudaStream_t);                                 \
+  template cudaError_t launch_schur_ell<T>(const Dev<T> &, int, const T *, T *, T *, int, cudaStream_t);      \
+  template cudaError_t launch_prep_ell<T>(const Dev<T> &, cudaStream_t);                                      \
+  template cudaError_t launch_trial_ell<T>(const Dev<T> &, cudaStream_t);                                     \
+  template cudaError_t launch_eval_edges_ell<T>(const Dev<T> &, T *, T *, cudaStream_t);                      \
+  template cudaError_t launch_pad_cam_T<T>(const Dev<T> &, const T *, cudaStream_t);                          \
+  template cudaError_t launch_permute3<T>(const T *, T *, const int *, int, int, cudaStream_t);
+BA_INSTANTIATE_ELL(double)
+BA_INSTANTIATE_ELL(float)
+
+}  // namespace ba

@@ -11,6 +11,27 @@
 // Points of this rank are numbered locally 0..nPl-1 (global id - pt_begin).
 // A second, camera-major view of the same edges (cm_*) feeds the atomic-free
 // accumulation of Hpp / g_c.
+//
+// ELL layout (the default; the tile layout above is kept as the measured baseline).  Local points are
+// sorted by observation count (descending) -- "device order" -- and cut into SLICES of 32 points; a slice
+// is the work of one warp, lane = point.  The observations of a slice are stored as D rows of 32 slots
+// (row r, lane l = r-th observation of the slice's l-th point, D = largest count in the slice, padding
+// slots carry camera -1), so that every per-observation stream is read with fully coalesced loads while
+// all per-point quantities (X, Hll^-1, t, u) stay in the registers of ONE thread: no shared-memory
+// segment sums, no block barriers.  A point with more than ELL_HEAVY observations gets a warp of its own
+// (lane = observation, row r holds its observations 32r .. 32r+31).  Per-slot arrays:
+//   r_cam[row][32] int32, r_obs[row][32][2], r_info[row][32][4] (optional),
+//   operator stream, row-blocked:  value pair j of slot (row, l) at  ((row*K/2 + j)*32 + l)*2, i.e. a warp
+//   reads K/2 consecutive 512-byte (fp64) runs per row and a slice is one contiguous run of D*K*32 scalars.
+// Operator stream flavours (Dev::store):
+//   ST_W (tile layout only)  K = 27  the Hpl block W = Jc^T Omega Jp of the observation
+//   ST_J                     K = 24  the 2x12 Jacobian
+//   ST_FACT (ELL only)       K = 8   Jp (2x3) and the normalised image point B (2): with the per-camera
+//        block-diagonal map  T_c = diag(Jr(omega), R^T, E(f,k1,k2))  one has  Jc = [Jp (.)x X-form | ...]:
+//          Jc x = Jp (psi x X + xt) + B (e0 + l2 e1 + l2^2 e2),   (psi, xt, e) = T_c x,   l2 = |B|^2
+//          Jc^T z = T_c^T ( X x v, v, (B.z)(1, l2, l2^2) ),        v = Jp^T z
+//        (Jr = right Jacobian of SO(3): R^T dR(omega)[x] = [Jr x]x), so the S*p pass streams 64 instead
+//        of 216 bytes per observation and the camera kernel applies T_c / T_c^T to its 9-vectors.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,6 +44,11 @@ constexpr int CM_THREADS = 128;
 constexpr int NTRI = 45;       // upper triangle of a 9x9 block
 constexpr int NREP = 16;        // replicas of the camera-space scatter target (spreads REDs over L2 slices)
 constexpr int AUX_GRID = 296;   // 2 CTAs per SM for the small grid-stride kernels
+constexpr int ELL_HEAVY = 32;   // points with more observations than this get a warp of their own
+constexpr int ELL_WARPS = 8;    // warps (slices) per CTA of the ELL kernels
+constexpr int CAMC = 16;        // per-camera constants for the edge kernels: cam[9], c, a, b, a', b', small, pad
+constexpr int CAMT = 27;        // per-camera transform blocks of the factored operator: Jr[9], R[9], E[9]
+enum Store { ST_W = 1, ST_J = 2, ST_FACT = 3 };
 
 template <typename T> struct CamPad;
 template <> struct CamPad<double> { static constexpr int N = 10; using vec = double2; };  // 80 B rows
@@ -46,7 +72,7 @@ struct PeerExchange {
 
 // device scalar slots (double) read back by the host
 enum Scal { S_COST = 0, S_TRIAL_COST = 1, S_MODEL_SQ = 2, S_DX2_PT = 3, S_X2_PT = 4, S_DX2_CAM = 5,
-            S_X2_CAM = 6, S_GINF = 7, S_XCHG_ERR = 15, S_COUNT = 16 };
+            S_X2_CAM = 6, S_GINF = 7, S_ANY_SMALL = 8, S_XCHG_ERR = 15, S_COUNT = 16 };
 
 template <typename T>
 struct Dev {
@@ -60,6 +86,15 @@ struct Dev {
   const T *e_obs;               // [slot][2]
   const T *e_info;              // [slot][4] or nullptr
   const int *pt_slot;           // [nPl] first slot of the point
+  // ELL static graph (ell != 0; the tile fields above are then unused)
+  int ell, store, nW, nRows, nPlPad;
+  const int4 *wdesc;            // per warp: {first row, rows D, first point (device order), kind | np << 8}
+  const int *r_cam;             // [nRows][32] camera of the slot, -1 = padding
+  const T *r_obs;               // [nRows][32][2]
+  const T *r_info;              // [nRows][32][4] or nullptr
+  T *camc;                      // [nC][CAMC]
+  T *camT;                      // [nC][CAMT]
+  T *HllInvP, *wP, *XP;         // planes [9][nPlPad], [3][nPlPad], [3][nPlPad] (device order)
   // camera-major static graph
   const int4 *chunk;            // {cam, beg, end, 0}
   const int *cam_chunk_ptr;     // [nC+1]
@@ -91,6 +126,7 @@ struct Dev {
 
 // ---- launchers (ba_kernels.cu); all enqueue on `st` and return cudaGetLastError ----
 template <typename T> cudaError_t launch_linearize(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_lin_cm(const Dev<T> &d, cudaStream_t st);
 enum SchurMode { SM_FULL = 0, SM_MAKEV = 1, SM_BACKSUB = 2, SM_INIT = 3 };
 template <typename T> cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set,
                                                     int check_active, cudaStream_t st);
@@ -110,5 +146,17 @@ template <typename T> cudaError_t launch_eval_edges(const Dev<T> &d, T *r_slots,
 template <typename T> cudaError_t launch_cam_matvec_sub(const Dev<T> &d, const T *p, const T *s, T *q, cudaStream_t st);
 int launches_of_linearize();
 int launches_of_prep();
+// ---- ELL layout (ba_ell.cu)
+template <typename T> cudaError_t launch_cam_consts(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_linearize_ell(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_schur_ell(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set,
+                                                   int check_active, cudaStream_t st);
+template <typename T> cudaError_t launch_prep_ell(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_eval_edges_ell(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st);
+template <typename T> cudaError_t launch_pad_cam_T(const Dev<T> &d, const T *src, cudaStream_t st);
+template <typename T> cudaError_t launch_permute3(const T *src, T *dst, const int *perm, int n, int gather, cudaStream_t st);
+int launches_of_linearize_ell();
+bool pdl_enabled();
 
 }  // namespace ba

@@ -30,6 +30,7 @@
 
 #include "ba_geometry.cuh"
 #include "ba_internal.h"
+#include "ba_device_utils.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -44,37 +45,6 @@ namespace ba {
 #ifndef BA_DEFAULT_VAR
 #define BA_DEFAULT_VAR 5
 #endif
-
-// --------------------------------------------------------------------------------
-// small helpers
-template <typename T>
-__device__ __forceinline__ T warp_sum(T v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// Sum over the block; result valid in every thread.  sm: >= 32 entries.
-template <typename T>
-__device__ __forceinline__ T block_sum(T v, T *sm) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = warp_sum(v);
-  __syncthreads();  // protect sm from a previous use
-  if (lane == 0) sm[wid] = v;
-  __syncthreads();
-  T x = lane < nw ? sm[lane] : T(0);
-  x = warp_sum(x);
-  return x;
-}
-
-template <typename T>
-__device__ __forceinline__ size_t wj_base(int slot, int K) {
-  return (size_t)(slot / TE) * (size_t)(K * TE) + (size_t)(slot % TE);
-}
-
-template <typename T> struct Vec2;
-template <> struct Vec2<double> { using type = double2; };
-template <> struct Vec2<float> { using type = float2; };
 
 // per-edge evaluation shared by the linearisation kernels
 template <typename T>
@@ -263,32 +233,6 @@ __global__ void __launch_bounds__(64) k_lin_cam_reduce(Dev<T> d) {
   }
 }
 
-// Deterministic final reduction of per-CTA partials: out[j] = op_i part[i*ncomp + j].
-template <int OP>  // 0 sum, 1 max
-__global__ void __launch_bounds__(1024) k_reduce(const double *__restrict__ part, int n, int ncomp, double *out) {
-  __shared__ double sm[32];
-  for (int j = 0; j < ncomp; ++j) {
-    double v = 0.;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const double x = part[(size_t)i * ncomp + j];
-      v = OP == 0 ? v + x : fmax(v, x);
-    }
-    if (OP == 0) {
-      v = block_sum<double>(v, sm);
-    } else {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-      __syncthreads();
-      v = (threadIdx.x & 31) < (blockDim.x >> 5) ? sm[threadIdx.x & 31] : 0.;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    }
-    if (threadIdx.x == 0) out[j] = v;
-  }
-}
-
 // --------------------------------------------------------------------------------
 // Solve preparation
 template <typename T>
@@ -392,45 +336,6 @@ __device__ __forceinline__ void edge_scatter(const T *wj, const T *u, T *out9) {
   }
 }
 
-// Camera-side scatter of one warp's 32 x 9 values.  The values are staged through shared memory so
-// that consecutive lanes add consecutive components of one camera (3 RED sectors per observation
-// instead of 9), and the target vector exists in NREP replicas selected by CTA so the RED traffic is
-// spread over all L2 slices (profiles/r01_microbench_red.txt: 0.47 ms -> 0.087 ms for Venice).
-template <typename T>
-__device__ __forceinline__ void warp_scatter9(T *sv, int *sc, const T *o, int c, T *dst) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  T *mine = sv + (size_t)w * 32 * 9;
-  int *cams = sc + w * 32;
-  cams[lane] = c;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) mine[lane * 9 + k] = o[k];
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    const int v = j * 32 + lane, el = v / 9, k = v - 9 * el;
-    const int cc = cams[el];
-    if (cc >= 0) atomicAdd(dst + 9 * (size_t)cc + k, mine[v]);
-  }
-  __syncwarp();
-}
-
-// Camera-space vectors consumed by the edge kernel are kept in a padded copy (stride CamPad::N scalars,
-// 16-byte aligned rows) so that one lane fetches its camera's 9 values with 16-byte loads.
-template <typename T, bool VEC>
-__device__ __forceinline__ void gather_cam(const T *__restrict__ xpad, int c, T *x) {
-  const T *src = xpad + (size_t)CamPad<T>::N * c;
-  if (VEC) {
-    using V = typename CamPad<T>::vec;
-    constexpr int NV = CamPad<T>::N * sizeof(T) / 16;
-    V *xv = reinterpret_cast<V *>(x);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) xv[k] = __ldg(reinterpret_cast<const V *>(src) + k);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) x[k] = __ldg(src + k);
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) k_pad_cam(const T *__restrict__ src, T *dst, int nC) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -438,14 +343,6 @@ __global__ void __launch_bounds__(256) k_pad_cam(const T *__restrict__ src, T *d
   const int c = i / 9, k = i - 9 * c;
   dst[(size_t)CamPad<T>::N * c + k] = src[i];
 }
-
-template <int N>
-__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gsrc), "n"(N) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // VAR bits.  The shipped kernel is VAR = 5; VAR = 0 (env BA_VAR=0) is kept as the measured baseline
 // (profiles/r01_edge_variants_padded_gather.txt).
@@ -682,10 +579,13 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, T *sB, int ma
   cg::cluster_group cl = cg::this_cluster();
   __shared__ double red_warp[32];
   __shared__ double slots[2];
+  // launched with the programmatic-serialisation attribute like the register-resident flavour: the preceding edge
+  // pass (replica sums, p, state) must be complete before anything below is read
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   PcgState st;
   if (INIT) {
     st.rho = 0.; st.rho_prev = 0.; st.rho_min = INFINITY; st.alpha = 0.; st.pq = 0.;
-    st.tol = tol; st.refuse = refuse; st.n = 0; st.max_iter = max_iter; st.active = 1; st.done = 0; st.refused = 0;
+    st.tol = tol; st.refuse = refuse; st.n = 0; st.max_iter = max_iter > 1 ? max_iter : 1; st.active = 1; st.done = 0; st.refused = 0;
   } else {
     st = *d.st;
     if (!st.active) return;  // uniform over the cluster: st is only written after the last cluster.sync
@@ -755,9 +655,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_cam(Dev<T> d, T *sB, int ma
     st.n += 1;                                  // :405
     st.done = fabs(st.rho) < st.tol;            // :406 (rho of the iteration just finished)
     cont = !st.done && st.n < st.max_iter;      // :407
-  } else {
-    cont = st.max_iter > 0;
-  }
+  }  // INIT: the reference's do-while always enters its first iteration
   if (cont) {
     if (rho_new > st.refuse * st.rho_min) {     // :288-295
       st.refused = 1;
@@ -848,12 +746,28 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
   T *r_s = p_s + RPT * PCG_THREADS;
   T *hi_s = r_s + RPT * PCG_THREADS;  // [RPT*PCG_THREADS][9], only when !PRE_INV
   T hd[RPT][9], hi[PRE_INV ? RPT : 1][9], pj[RPT], rj[RPT], xj[RPT], xb[RPT], sj[RPT], qj[RPT], zj[RPT];
+  // Factored operator stream (ba_internal.h): the edge pass gathers T_c p and scatters Y with s = T_c^T Y, T_c block
+  // diagonal (3x3 blocks Jr, R^T, E).  tin = row k of T_c, tout = column k of T_c (within the row's block).
+  const bool fact = d.store == ST_FACT;
+  T tin[RPT][3], tout[RPT][3];
   // ---- loads that do not depend on the preceding edge pass: the rows of the damped Hpp and of its inverse
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     const int l = tid + j * PCG_THREADS;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) tin[j][m] = tout[j][m] = T(0);
     if (l < nrows) {
       const int i = i0 + l, c = i / 9, k = i - 9 * c;
+      if (fact) {
+        const int bk = k / 3, kk = k - 3 * bk;
+        const T *tb = d.camT + (size_t)CAMT * c + 9 * bk;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          const T rowv = __ldg(tb + 3 * kk + m), colv = __ldg(tb + 3 * m + kk);
+          tin[j][m] = bk == 1 ? colv : rowv;   // block 1 of T_c is R^T, stored as R
+          tout[j][m] = bk == 1 ? rowv : colv;
+        }
+      }
 #pragma unroll
       for (int m = 0; m < 9; ++m) hd[j][m] = __ldg(d.HppD + 81 * (size_t)c + 9 * k + m);
       if (PRE_INV) {
@@ -869,7 +783,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
   PcgState st;
   if (INIT) {
     st.rho = 0.; st.rho_prev = 0.; st.rho_min = INFINITY; st.alpha = 0.; st.pq = 0.;
-    st.tol = tol; st.refuse = refuse; st.n = 0; st.max_iter = max_iter; st.active = 1; st.done = 0; st.refused = 0;
+    st.tol = tol; st.refuse = refuse; st.n = 0; st.max_iter = max_iter > 1 ? max_iter : 1; st.active = 1; st.done = 0; st.refused = 0;
   } else {
     st = *d.st;
     if (!st.active) return;
@@ -953,6 +867,22 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
       }
     }
   }
+  if (fact) {  // s = T_c^T Y: the three Y rows of this row's block come through shared memory
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PCG_THREADS;
+      if (l < nrows) r_s[l] = sj[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PCG_THREADS;
+      if (l < nrows) {
+        const int lb = l - ((i0 + l) % 9) % 3;
+        sj[j] = tout[j][0] * r_s[lb] + tout[j][1] * r_s[lb + 1] + tout[j][2] * r_s[lb + 2];
+      }
+    }
+  }
   __syncthreads();
   double acc = 0.;
 #pragma unroll
@@ -1008,9 +938,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
     st.n += 1;                                 // :405
     st.done = fabs(st.rho) < st.tol;           // :406
     cont = !st.done && st.n < st.max_iter;     // :407
-  } else {
-    cont = st.max_iter > 0;
-  }
+  }  // INIT: the reference's do-while always enters its first iteration (max_iter < 1 behaves like 1)
   T beta = T(0);
   if (cont) {
     if (rho_new > st.refuse * st.rho_min) {    // :288-295
@@ -1038,7 +966,21 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
       if (cont) {
         const T pv = INIT ? zj[j] : zj[j] + beta * pj[j];  // :310 / :299-306
         d.p[i] = pv;
-        d.xpad[(size_t)CamPad<T>::N * (i / 9) + i % 9] = pv;
+        if (fact) p_s[l] = pv;
+        else d.xpad[(size_t)CamPad<T>::N * (i / 9) + i % 9] = pv;
+      }
+    }
+  }
+  if (fact) {  // the edge pass gathers T_c p (cont and fact are uniform over the cluster / grid)
+    __syncthreads();
+    if (cont) {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const int l = tid + j * PCG_THREADS;
+        if (l < nrows) {
+          const int i = i0 + l, lb = l - (i % 9) % 3;
+          d.xpad[(size_t)CamPad<T>::N * (i / 9) + i % 9] = tin[j][0] * p_s[lb] + tin[j][1] * p_s[lb + 1] + tin[j][2] * p_s[lb + 2];
+        }
       }
     }
   }
@@ -1194,19 +1136,34 @@ __global__ void __launch_bounds__(256) k_cam_matvec_sub(Dev<T> d, const T *p, co
   T a = T(0);
 #pragma unroll
   for (int j = 0; j < 9; ++j) a += d.HppD[81 * (size_t)c + 9 * k + j] * p[9 * c + j];
-  q[i] = a - s[i];
+  T sv = s[i];
+  if (d.store == ST_FACT) {  // s holds Y; apply T_c^T (see k_pcg_cam_reg)
+    const int bk = k / 3, kk = k - 3 * bk;
+    const T *tb = d.camT + (size_t)CAMT * c + 9 * bk;
+    const T *y = s + 9 * (size_t)c + 3 * bk;
+    sv = bk == 1 ? tb[3 * kk] * y[0] + tb[3 * kk + 1] * y[1] + tb[3 * kk + 2] * y[2]
+                 : tb[kk] * y[0] + tb[3 + kk] * y[1] + tb[6 + kk] * y[2];
+  }
+  q[i] = a - sv;
 }
 
 // --------------------------------------------------------------------------------
 // launchers
+// camera side of the linearisation (layout-independent: it walks the camera-major view)
+template <typename T>
+cudaError_t launch_lin_cm(const Dev<T> &d, cudaStream_t st) {
+  if (d.nChunks > 0) k_lin_cm<T><<<d.nChunks, CM_THREADS, 0, st>>>(d);
+  k_lin_cam_reduce<T><<<d.nC, 64, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_linearize(const Dev<T> &d, cudaStream_t st) {
   if (d.nT > 0) {
     if (d.implicit) k_lin_pm<T, true><<<d.nT, TE, 0, st>>>(d);
     else k_lin_pm<T, false><<<d.nT, TE, 0, st>>>(d);
   }
-  if (d.nChunks > 0) k_lin_cm<T><<<d.nChunks, CM_THREADS, 0, st>>>(d);
-  k_lin_cam_reduce<T><<<d.nC, 64, 0, st>>>(d);
+  launch_lin_cm<T>(d, st);
   k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nT, 1, d.scal + S_COST);
   return cudaGetLastError();
 }
@@ -1214,7 +1171,7 @@ int launches_of_linearize() { return 4; }
 
 template <typename T>
 cudaError_t launch_prep(const Dev<T> &d, cudaStream_t st) {
-  if (d.nPl > 0) k_prep_points<T><<<(d.nPl + 255) / 256, 256, 0, st>>>(d);
+  if (d.nPl > 0 && !d.ell) k_prep_points<T><<<(d.nPl + 255) / 256, 256, 0, st>>>(d);  // ELL: launch_prep_ell
   k_prep_cams<T><<<(d.nC + 63) / 64, 64, 0, st>>>(d);
   return cudaGetLastError();
 }
@@ -1482,6 +1439,7 @@ cudaError_t launch_cam_matvec_sub(const Dev<T> &d, const T *p, const T *s, T *q,
 
 #define BA_INSTANTIATE(T)                                                                                   \
   template cudaError_t launch_linearize<T>(const Dev<T> &, cudaStream_t);                                   \
+  template cudaError_t launch_lin_cm<T>(const Dev<T> &, cudaStream_t);                                      \
   template cudaError_t launch_schur_edge<T>(const Dev<T> &, int, const T *, T *, T *, int, cudaStream_t);   \
   template cudaError_t launch_prep<T>(const Dev<T> &, cudaStream_t);                                        \
   template cudaError_t launch_pcg_init<T>(const Dev<T> &, T *, int, double, double, int, const PeerExchange &, cudaStream_t); \

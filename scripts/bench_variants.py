@@ -1,5 +1,6 @@
-"""Time the S*p edge kernel for each design variant (env BA_VAR) on the Venice-shaped problem.
-Usage: python scripts/bench_variants.py 0 2 4 6 ...   (each variant runs in its own process)"""
+"""Time the S*p edge kernel for each design variant on the Venice-shaped problem, one process per variant.
+Usage: python scripts/bench_variants.py 0 5 ...                      (tile layout: env BA_VAR)
+       python scripts/bench_variants.py BA_LAYOUT=tile BA_ELL_RC=0,BA_PDL=0 ...   (any environment settings)"""
 import os
 import subprocess
 import sys
@@ -13,8 +14,6 @@ def child():
     import numpy as np
     from megba_b200 import capi
     from megba_b200.synthetic import BAProblem
-    if os.environ.get("BA_LIB"):  # an experimental build of the same library (e.g. build/exp/libmegba_b200_g32.so)
-        capi.LIB_PATH = os.path.join(ROOT, os.environ["BA_LIB"])
     if os.environ.get("BA_LIB"):  # an experimental build of the same library (e.g. build/exp/libmegba_b200_g32.so)
         capi.LIB_PATH = os.path.join(ROOT, os.environ["BA_LIB"])
     z = np.load(CACHE)
@@ -32,7 +31,7 @@ def child():
     st = S.stats()
     a_pcg, _ = S.algorithmic_bytes()
     k = st["schur_apply_ms"] / st["schur_apply_timed"]
-    print(f"VAR={os.environ.get('BA_VAR','-')} LIB={os.environ.get('BA_LIB','default')} edge {k*1e3:8.1f} us  {a_pcg/k/1e6:7.0f} GB/s   pcg loop "
+    print(f"{os.environ.get('BA_SPEC','-'):28s} edge {k*1e3:8.1f} us  {a_pcg/k/1e6:7.0f} GB/s   pcg loop "
           f"{st['pcg_loop_ms']/st['pcg_iters']*1e3:7.1f} us/iter   cam kernel {st['pcg_cam_ms']/max(st['pcg_cam_timed'],1)*1e3:6.1f} us   "
           f"solve {st['solve_ms']/3:7.2f} ms", flush=True)
     print(f"        check: |dx|, |x| = {S.step_norms()}", flush=True)  # must agree between variants to ~1e-12 relative
@@ -57,5 +56,9 @@ if __name__ == "__main__":
         P = make_named(os.environ.get("BA_WORKLOAD", "venice-1778"))
         np.savez(CACHE, nC=P.nC, nP=P.nP, nE=P.nE, cam_idx=P.cam_idx, pt_idx=P.pt_idx, obs=P.obs, cam=P.cam, pt=P.pt)
     for v in sys.argv[1:] or ["0"]:
-        env = dict(os.environ, BA_VAR=v, BA_CHILD="1")
+        env = dict(os.environ, BA_CHILD="1", BA_SPEC=v)
+        if "=" in v:
+            env.update(kv.split("=", 1) for kv in v.split(","))
+        else:
+            env.update(BA_VAR=v, BA_LAYOUT="tile")
         subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/megba_b200.h but not exported"
     assert sorted(capi.SYMBOLS) == declared
-    assert L.ba_abi_version() == 1
+    assert L.ba_abi_version() == 2
 
 
 def test_partition_points_balances_edges_and_keeps_points_whole():

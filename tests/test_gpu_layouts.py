@@ -1,0 +1,135 @@
+"""GPU parity of every (layout, operator stream) flavour of the hot path against the CPU oracle.
+
+The default of ba_create is the ELL layout with the factored operator stream; the tile layout
+with the W / J streams is the measured baseline, and the ELL layout can also stream the full Jacobian (which it does
+by itself while any camera is in the small-angle branch).  test_gpu_parity.py runs everything on the default; this
+file runs the linear-algebra core on every flavour so that none of them can rot."""
+import numpy as np
+import pytest
+
+from megba_b200 import capi
+from oracle.oracle import Oracle
+from util import TOL, bigpoint_problem, medium_problem, rel_fro, small_problem
+
+pytestmark = pytest.mark.gpu
+
+# (layout, store, implicit)
+FLAVOURS = {
+    "ell-fact": (capi.LAYOUT_ELL, capi.STORE_FACT, False),
+    "ell-fact-implicit-kind": (capi.LAYOUT_ELL, capi.STORE_FACT, True),
+    "ell-j": (capi.LAYOUT_ELL, capi.STORE_J, False),
+    "tile-w": (capi.LAYOUT_TILE, capi.STORE_AUTO, False),
+    "tile-j": (capi.LAYOUT_TILE, capi.STORE_AUTO, True),
+}
+PROBLEMS = {"small": small_problem, "medium": medium_problem, "bigpoint": bigpoint_problem}
+
+
+def _solver(P, dtype, flavour):
+    layout, store, implicit = FLAVOURS[flavour]
+    S = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype=dtype, implicit=implicit, layout=layout, store=store)
+    S.set_params(P.cam, P.pt)
+    return S
+
+
+def _oracle_step(P, dtype, region, n_it, info=None, dx0=None):
+    O = Oracle(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype)
+    r, J = O.forward(P.cam, P.pt)
+    Hpp, Hll, W, g = O.build(r, J, info=info)
+    HppD, _ = O.process_diag(Hpp, region)
+    HllD, _ = O.process_diag(Hll, region)
+    x0 = np.zeros(9 * P.nC + 3 * P.nP) if dx0 is None else dx0
+    dx, it, _, _ = O.schur_pcg(HppD, HllD, W, None, g, x0, n_it, 0.0, 1e300)
+    return O, (r, J, Hpp, Hll, W, g, HppD, HllD), dx, it
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["small", "medium", "bigpoint"])
+@pytest.mark.parametrize("flavour", list(FLAVOURS))
+def test_flavour_linearize_operator_pcg(flavour, name, dtype):
+    P = PROBLEMS[name]()
+    S = _solver(P, dtype, flavour)
+    t = TOL[np.dtype(dtype)]
+    region, n_it = 1e3, 10
+    O, (r, J, Hpp, Hll, W, g, HppD, HllD), dx0, it0 = _oracle_step(P, dtype, region, n_it)
+    cost = S.linearize()
+    assert abs(cost - O.cost(r)) <= t["cost"] * O.cost(r)
+    assert rel_fro(S.read(capi.BUF_HPP), Hpp) <= t["H"]
+    assert rel_fro(S.read(capi.BUF_HLL), Hll) <= t["H"]
+    assert rel_fro(S.read(capi.BUF_G), g) <= t["H"]
+    S.process_diag(region)
+    p = np.random.default_rng(3).normal(size=9 * P.nC)
+    q = S.schur_apply(p)
+    q0 = O.schur_mul(HppD, O.block_inverse(HllD), W, None, p)
+    assert rel_fro(q, q0) <= 10 * t["H"]
+    it, _ = S.solve(max_iter=n_it, tol=0.0, refuse_ratio=1e300)
+    assert it == it0 == n_it
+    assert rel_fro(S.read(capi.BUF_DX), dx0) <= t["dx"]
+    # a second solve warm-starts from the first (schur_pcg_solver.cu:193,206) -- exercises the INIT pass on x0 != 0
+    _, _, dx1, _ = _oracle_step(P, dtype, region, 4, dx0=dx0)
+    S.solve(max_iter=4, tol=0.0, refuse_ratio=1e300)
+    assert rel_fro(S.read(capi.BUF_DX), dx1) <= 10 * t["dx"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("flavour", ["ell-fact", "ell-fact-implicit-kind", "ell-j", "tile-w"])
+def test_flavour_information_matrices(flavour, dtype):
+    """H = J^T Omega J through every stream that supports it -- including the implicit compute kind of the ELL
+    layout (upstream's implicit build silently ignores Omega, build_implicit_linear_system.cu:272-274)."""
+    P = small_problem()
+    rng = np.random.default_rng(11)
+    a, b, c = rng.uniform(0.5, 2.0, P.nE), rng.uniform(-0.3, 0.3, P.nE), rng.uniform(0.5, 2.0, P.nE)
+    info = np.stack([a, b, b, c], axis=1)
+    S = _solver(P, dtype, flavour)
+    S.set_information(info)
+    t = TOL[np.dtype(dtype)]
+    region, n_it = 1e3, 8
+    O, (r, J, Hpp, Hll, W, g, HppD, HllD), dx0, it0 = _oracle_step(P, dtype, region, n_it, info=info)
+    S.linearize()
+    assert rel_fro(S.read(capi.BUF_HPP), Hpp) <= t["H"]
+    assert rel_fro(S.read(capi.BUF_HLL), Hll) <= t["H"]
+    assert rel_fro(S.read(capi.BUF_G), g) <= t["H"]
+    S.process_diag(region)
+    p = np.random.default_rng(5).normal(size=9 * P.nC)
+    q0 = O.schur_mul(HppD, O.block_inverse(HllD), W, None, p)
+    assert rel_fro(S.schur_apply(p), q0) <= 10 * t["H"]
+    S.solve(max_iter=n_it, tol=0.0, refuse_ratio=1e300)
+    assert rel_fro(S.read(capi.BUF_DX), dx0) <= t["dx"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_small_angle_camera_falls_back_to_the_jacobian_stream(dtype):
+    """A camera with theta^2 <= eps takes the reference's first-order branch (analytical_derivatives.cu:131-158), where
+    R = I + [omega]x is not a rotation; the factored stream then gives way to the Jacobian stream for that linearisation
+    and returns once the camera has moved on."""
+    P = small_problem()
+    cam = P.cam.copy()
+    cam[2, :3] = 0.0
+    cam[5, :3] = [1e-9, -2e-9, 5e-10]
+    Q = type(P)(P.nC, P.nP, P.nE, P.cam_idx, P.pt_idx, P.obs, cam, P.pt, "small-angle")
+    S = _solver(Q, dtype, "ell-fact")
+    t = TOL[np.dtype(dtype)]
+    region, n_it = 1e3, 10
+    O, sysm, dx0, _ = _oracle_step(Q, dtype, region, n_it)
+    S.linearize()
+    S.process_diag(region)
+    S.solve(max_iter=n_it, tol=0.0, refuse_ratio=1e300)
+    assert rel_fro(S.read(capi.BUF_DX), dx0) <= t["dx"]
+    a_pcg_small, _ = S.algorithmic_bytes()
+    # LM moves the cameras away from the degenerate branch: the trace must match the oracle's
+    S.set_params(Q.cam, Q.pt)  # deltaX back to zero (the solve above would warm-start the first PCG)
+    tr = S.lm_solve(lm_max_iter=4, initial_region=1e3, pcg_max_iter=20, pcg_tol=0.0, pcg_refuse=1e300, eps1=0.0, eps2=0.0)
+    _, _, tr0 = O.lm_solve(Q.x(dtype), lm_max_iter=4, initial_region=1e3, eps1=0.0, eps2=0.0, pcg_max_iter=20,
+                           pcg_tol=0.0, pcg_refuse=1e300)
+    assert [r["accepted"] for r in tr] == [r["accepted"] for r in tr0]
+    for a, b in zip(tr, tr0):
+        assert abs(a["cost"] - b["cost"]) <= 50 * t["cost"] * abs(b["cost"])
+    a_pcg_after, _ = S.algorithmic_bytes()
+    assert a_pcg_after < a_pcg_small  # back on the 8-scalar stream
+
+
+def test_layout_store_combinations_are_validated():
+    P = small_problem()
+    with pytest.raises(RuntimeError):
+        capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, layout=capi.LAYOUT_ELL, store=capi.STORE_W)
+    with pytest.raises(RuntimeError):
+        capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, layout=capi.LAYOUT_TILE, store=capi.STORE_FACT)

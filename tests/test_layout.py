@@ -88,3 +88,62 @@ def test_layout_rejects_bad_input():
         capi.layout(2, 2, np.array([0, 5], np.int32), np.array([0, 1], np.int32))  # camera index out of range
     with pytest.raises(RuntimeError):
         capi.layout(1 << 24, 2, np.array([0], np.int32), np.array([0], np.int32))  # camera count beyond the packed index
+
+
+@pytest.mark.parametrize("name", ["small", "bigpoint", "ragged", "single_obs_points", "empty"])
+@pytest.mark.parametrize("ws", [1, 2, 3])
+def test_ell_layout_invariants(name, ws):
+    """The default (ELL) layout: device order sorted by observation count, heavy points in warps of their own,
+    slices of 32 points with one row per observation rank, every observation in exactly one slot of one rank."""
+    nC, nP, cam_idx, pt_idx = _problems()[name]
+    nE = len(cam_idx)
+    deg = np.bincount(pt_idx, minlength=nP)
+    cuts = capi.partition_points(deg, ws)
+    seen = np.zeros(nE, np.int32)
+    for rank in range(ws):
+        L = capi.layout_ell(nC, nP, cam_idx, pt_idx, rank, ws)
+        warp, perm, eos, scam = L["warp"], L["perm"], L["edge_of_slot"], L["slot_cam"]
+        nPl = cuts[rank + 1] - cuts[rank]
+        assert L["pt_begin"] == cuts[rank] and len(perm) == nPl
+        assert sorted(perm.tolist()) == list(range(nPl))  # a permutation of the local points
+        ldeg = deg[cuts[rank] + perm] if nPl else np.zeros(0, np.int64)
+        assert np.all(np.diff(ldeg) <= 0)  # descending observation count
+        assert L["n_heavy"] == int((ldeg > 32).sum())
+        assert len(eos) == 32 * L["n_rows"] and len(scam) == len(eos)
+        row = 0
+        next_pt = 0
+        for w, (row0, D, pt0, kw) in enumerate(warp):
+            kind, npts = kw & 0xFF, kw >> 8
+            assert row0 == row and pt0 == next_pt  # rows and points are consumed in order, without gaps
+            if kind == 1:  # heavy point: lane = observation
+                assert w < L["n_heavy"] and npts == 1 and D == -(-ldeg[pt0] // 32)
+                slots = eos[32 * row0: 32 * (row0 + D)]
+                assert np.all(slots[: ldeg[pt0]] >= 0) and np.all(slots[ldeg[pt0]:] == -1)
+                assert np.all(pt_idx[slots[: ldeg[pt0]]] == cuts[rank] + perm[pt0])
+            else:  # slice: lane = point, row r = r-th observation of each point
+                assert 1 <= npts <= 32 and D == ldeg[pt0]
+                blk = eos[32 * row0: 32 * (row0 + D)].reshape(D, 32)
+                for lane in range(32):
+                    col = blk[:, lane]
+                    d = ldeg[pt0 + lane] if lane < npts else 0
+                    assert np.all(col[:d] >= 0) and np.all(col[d:] == -1)
+                    if d:
+                        assert np.all(pt_idx[col[:d]] == cuts[rank] + perm[pt0 + lane])
+                        assert np.all(np.diff(cam_idx[col[:d]]) >= 0)  # camera-ascending inside a point
+            row += D
+            next_pt += npts
+        assert row == L["n_rows"] and next_pt == nPl
+        valid = eos >= 0
+        assert np.array_equal(scam[valid], cam_idx[eos[valid]]) and np.all(scam[~valid] == -1)
+        np.add.at(seen, eos[valid], 1)
+        # camera-major view: chunks partition it, every entry points at a slot of that camera
+        chunk, cms = L["chunk"], L["cm_slot"]
+        assert len(cms) == valid.sum()
+        pos = 0
+        for cam, beg, end, _ in chunk:
+            assert beg == pos and 0 < end - beg <= CM_CHUNK
+            assert np.all(scam[cms[beg:end]] == cam)
+            pos = end
+        assert pos == len(cms)
+        assert len(np.unique(cms)) == len(cms)
+    assert np.all(seen == 1)
