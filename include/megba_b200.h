@@ -148,7 +148,8 @@ int ba_layout(const ba_options *opt, int64_t nC, int64_t nP, int64_t nE, const i
  * order"); points with more than 32 observations come first and get a warp each, the rest are cut into slices of
  * 32 points (lane = point).  Observation r of the slice's l-th point sits in slot (row0 + r) * 32 + l; observation
  * i of a heavy point in slot row0 * 32 + i.
- *   warp[n_warps][4]      = {first row, rows, first point (device order), kind | points << 8}, kind 1 = heavy point
+ *   warp[n_warps][4]      = {first row, rows, first point (device order), kind | points << 8 | stage row << 16},
+ *                           kind 1 = heavy point; stage row = the slice's place in its CTA's shared-memory stage
  *   perm[n_local_points]  = local point (global id - pt_begin) at each device position
  *   edge_of_slot / slot_cam[n_slots] = observation number (-1 padding) and camera (-1 padding) of the slot
  *   chunk / cm_slot       = camera-major view as in ba_layout                                                  */

@@ -62,6 +62,8 @@ struct HostGraph {
   int nW = 0, nRows = 0, nHeavy = 0;
   std::vector<int4> wdesc;             // {first row, rows, first point (device order), kind | np << 8}
   std::vector<int> perm;               // device position -> local point
+  std::vector<int2> cdesc;             // CTAs of the TMA-staged edge pass: {first warp, warps}; staged rows per CTA <= tma_rows
+  int tma_rows = 0;
 };
 
 // ba_options::layout / operator_store (0 = auto) and the BA_LAYOUT / BA_STORE environment overrides (experiments).
@@ -144,6 +146,28 @@ static int build_ell(int64_t nC, int64_t nE, const int32_t *cam_idx, const std::
   }
   g.nW = (int)g.wdesc.size();
   g.nRows = (int)rows;
+  // CTAs of the TMA-staged edge pass: consecutive warps whose slices' rows fit the CTA's shared-memory stage
+  // (tma_rows rows, at most ELL_WARPS warps); heavy points and slices longer than the stage stream from global memory
+  // and take no stage rows.  The warp's first stage row goes into bits 16.. of the descriptor (0xffff = not staged).
+  {
+    static const int rows_env = getenv("BA_TMA_ROWS") ? atoi(getenv("BA_TMA_ROWS")) : 0;
+    g.tma_rows = rows_env > 0 ? std::min(rows_env, 64) : 24;
+    g.cdesc.clear();
+    int first = 0, used = 0;
+    for (int w = 0; w < g.nW; ++w) {
+      int4 &wd = g.wdesc[w];
+      const bool staged = (wd.w & 0xff) == 0 && wd.y <= g.tma_rows;
+      const int need = staged ? wd.y : 0;
+      if (w - first == ELL_WARPS || used + need > g.tma_rows) {
+        g.cdesc.push_back(make_int2(first, w - first));
+        first = w;
+        used = 0;
+      }
+      wd.w |= (staged ? used : 0xffff) << 16;
+      used += need;
+    }
+    if (g.nW > first) g.cdesc.push_back(make_int2(first, g.nW - first));
+  }
   const size_t nSlots = (size_t)rows * 32;
   g.e_cam.assign(nSlots, -1);
   g.edge_of_slot.assign(nSlots, -1);
@@ -153,7 +177,7 @@ static int build_ell(int64_t nC, int64_t nE, const int32_t *cam_idx, const std::
   std::vector<int> slot_pt(nSlots, 0);
   for (const int4 &wd : g.wdesc) {
     const bool heavy = (wd.w & 0xff) != 0;
-    const int np = wd.w >> 8;
+    const int np = (wd.w >> 8) & 0xff;
     for (int l = 0; l < (heavy ? 1 : np); ++l) {
       const int kd = wd.z + l, pn = g.perm[kd];
       for (int64_t i = 0; i < ptr[pn + 1] - ptr[pn]; ++i) {
@@ -509,9 +533,10 @@ struct ImplT : Impl {
     int4 *tile, *chunk; int *e_cam, *pt_slot, *cam_chunk_ptr, *cm_pt; unsigned short *e_lp; T *e_obs, *cm_obs;
     auto add = [&](auto **p, size_t count) { items.push_back({(void **)p, count * sizeof(**p)}); };
     int4 *wdesc = nullptr;
+    int2 *cdesc = nullptr;
     add(&tile, g.nT); add(&e_cam, nSlots); add(&e_lp, ell ? 0 : nSlots); add(&e_obs, 2 * nSlots); add(&pt_slot, ell ? 0 : nPl);
     if (ell) {
-      add(&wdesc, g.nW); add(&d.camc, (size_t)CAMC * nC); add(&d.camT, (size_t)CAMT * nC);
+      add(&wdesc, g.nW); add(&cdesc, g.cdesc.size()); add(&d.camc, (size_t)CAMC * nC); add(&d.camT, (size_t)CAMT * nC);
       add(&d.HllInvP, 9 * nPlPad); add(&d.wP, 3 * nPlPad); add(&d.XP, 3 * nPlPad);
       add(&perm_dev, nPl); add(&pt_nat, 3 * nPl);
     }
@@ -542,7 +567,7 @@ struct ImplT : Impl {
     d.nC = (int)nC; d.nPl = (int)nPl; d.nT = g.nT; d.nSlabs = g.nSlabs; d.nChunks = g.nChunks; d.nEl = g.nEl;
     d.implicit = opt.compute_kind == BA_IMPLICIT;
     d.ell = ell; d.nW = g.nW; d.nRows = g.nRows; d.nPlPad = (int)nPlPad;
-    d.wdesc = wdesc; d.r_cam = e_cam; d.r_obs = e_obs; d.r_info = nullptr;
+    d.wdesc = wdesc; d.cdesc = cdesc; d.nCta = (int)g.cdesc.size(); d.tma_rows = g.tma_rows; d.r_cam = e_cam; d.r_obs = e_obs; d.r_info = nullptr;
     if (ell) {
       // the factored stream needs the register-resident camera kernel (it applies T_c / T_c^T)
       if (store_cfg == ST_FACT && !pcg_reg_kernel_available<T>(d)) store_cfg = ST_J;
@@ -571,6 +596,7 @@ struct ImplT : Impl {
     BA_CUDA(up(e_obs, h_obs.data(), sizeof(T) * 2 * nSlots));
     if (ell) {
       BA_CUDA(up(wdesc, g.wdesc.data(), sizeof(int4) * g.nW));
+      BA_CUDA(up(cdesc, g.cdesc.data(), sizeof(int2) * g.cdesc.size()));
       BA_CUDA(up(perm_dev, g.perm.data(), sizeof(int) * nPl));
     } else {
       BA_CUDA(up(e_lp, g.e_lp.data(), sizeof(unsigned short) * nSlots));

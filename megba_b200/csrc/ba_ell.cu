@@ -26,10 +26,10 @@ namespace ba {
 
 constexpr int ELL_THREADS = ELL_WARPS * 32;
 
-struct WDesc { int row0, D, pt0, heavy, np; };
+struct WDesc { int row0, D, pt0, heavy, np, soff; };
 __device__ __forceinline__ WDesc load_desc(const int4 *wdesc, int w) {
   const int4 v = __ldg(wdesc + w);
-  return WDesc{v.x, v.y, v.z, v.w & 0xff, v.w >> 8};
+  return WDesc{v.x, v.y, v.z, v.w & 0xff, (v.w >> 8) & 0xff, (int)((unsigned)v.w >> 16)};
 }
 
 // one camera's constants (CAMC scalars, 16-byte aligned rows) with 16-byte loads
@@ -288,8 +288,17 @@ __host__ __device__ constexpr size_t schur_ell_smem() {
 //   phase 2: s[cam(e)] += W_e u_j            RED.ADD, staged per warp so that one RED covers consecutive components
 // RC rows of the factored stream are kept in registers between the phases; further rows (and the wider Jacobian
 // stream) are read again in phase 2 (an L2 hit: the slice was streamed microseconds earlier).
+// Resident warps per SM the register allocation aims at: 24 / 16 / 12 / 8 for RC = 0 / 2 / 4 / 6 rows of the factored
+// stream kept in registers between the phases.  Measured on Venice fp64 (profiles/r02_edge_variants.txt): more resident
+// warps beat fewer L2 re-reads (RC 0: 168.9 us with 4-warp CTAs and the Hll^-1 load issued after phase 1; RC 2: 170.8;
+// RC 4: 185.3; RC 6: 207.4 us), keeping the stream out of L1 (ld.global.nc.L1::no_allocate) costs 6-10 us.
+#ifndef BA_ELL_LATE_HI
+#define BA_ELL_LATE_HI 1
+#endif
+constexpr int ell_min_blocks(int rc) { return (rc == 0 ? 24 : rc <= 2 ? 16 : rc <= 4 ? 12 : 8) / ELL_WARPS > 0 ? (rc == 0 ? 24 : rc <= 2 ? 16 : rc <= 4 ? 12 : 8) / ELL_WARPS : 1; }
+
 template <typename T, int STORE, int MODE, bool INFO, int RC>
-__global__ void __launch_bounds__(ELL_THREADS, RC >= 4 ? 1 : 2)
+__global__ void __launch_bounds__(ELL_THREADS, ell_min_blocks(RC))
 k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
   constexpr int K = STORE == ST_FACT ? 8 : 24;
   constexpr int NC = RC > 0 ? RC : 1;
@@ -299,7 +308,7 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
   int *sc = reinterpret_cast<int *>(sv + ELL_WARPS * 32 * 9);
   const int tid = threadIdx.x, lane = tid & 31, w = blockIdx.x * ELL_WARPS + (tid >> 5);
   const bool wvalid = w < d.nW;
-  WDesc wd{0, 0, 0, 0, 0};
+  WDesc wd{0, 0, 0, 0, 0, 0xffff};
   if (wvalid) wd = load_desc(d.wdesc, w);
   const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
   const bool pvalid = wvalid && (wd.heavy || lane < wd.np);
@@ -323,14 +332,17 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
   T hi[9], wv[3] = {T(0), T(0), T(0)};
 #pragma unroll
   for (int k = 0; k < 9; ++k) hi[k] = T(0);
-  if (pvalid) {
+  auto load_point_blocks = [&]() {
+    if (pvalid) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInvP + k * npl + p);
-    if (MODE != SM_FULL) {
+      for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInvP + k * npl + p);
+      if (MODE != SM_FULL) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) wv[k] = __ldg(d.wP + k * npl + p);
+        for (int k = 0; k < 3; ++k) wv[k] = __ldg(d.wP + k * npl + p);
+      }
     }
-  }
+  };
+  if (!BA_ELL_LATE_HI) load_point_blocks();
   if (check_active) {
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the preceding camera kernel (p, state, replica sets) is complete
     if (!d.st->active) return;
@@ -364,6 +376,7 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
     load_stream<T, K>(d.WJ, row, lane, s);
     if (c >= 0) first(s, c, slot);
   }
+  if (BA_ELL_LATE_HI) load_point_blocks();
   if (wd.heavy) { t0 = warp_sum<T>(t0); t1 = warp_sum<T>(t1); t2 = warp_sum<T>(t2); }
   // ---- point step
   T u0 = hi[0] * t0 + hi[1] * t1 + hi[2] * t2;
@@ -400,6 +413,156 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
     T s[K];
     load_stream<T, K>(d.WJ, row, lane, s);
     second(s, c, slot);
+  }
+}
+
+// --------------------------------------------------------------------------------
+// TMA-staged flavour of the factored S*p pass.  A CTA owns up to ELL_WARPS consecutive slices whose rows fit its
+// shared-memory stage (host-side grouping, Dev::cdesc).  Lane 0 of every warp fetches the warp's whole slice -- one
+// contiguous run of D * 8 * 32 scalars plus D * 32 camera indices -- with two cp.async.bulk copies that complete on
+// the warp's own mbarrier; both phases then read the stream from shared memory.  Compared with k_schur_ell this
+// removes the second (L2) read of the stream, takes the stream's fills off the LSU data pipe (the limiter of the pass,
+// profiles/README.md) and puts the whole slice in flight without landing registers, before griddepcontrol.wait.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+
+template <typename T>
+__host__ __device__ constexpr size_t schur_tma_smem(int rows) {
+  // stage rows [rows][8*32] T, camera rows [rows][32] int, one mbarrier per warp, scatter staging
+  return (size_t)rows * (8 * 32 * sizeof(T) + 32 * sizeof(int)) + 128 + schur_ell_smem<T>();
+}
+
+#ifndef BA_TMA_MINB
+#define BA_TMA_MINB 2
+#endif
+template <typename T, int MODE, bool INFO>
+__global__ void __launch_bounds__(ELL_THREADS, BA_TMA_MINB)
+k_schur_tma(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
+  using V = typename Vec2<T>::type;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int rows_cap = d.tma_rows;
+  T *stage = reinterpret_cast<T *>(smem_raw);
+  int *cstage = reinterpret_cast<int *>(stage + (size_t)rows_cap * 256);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(cstage + (size_t)rows_cap * 32);
+  T *sv = reinterpret_cast<T *>(bars + 16);
+  int *sc = reinterpret_cast<int *>(sv + ELL_WARPS * 32 * 9);
+  const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  const int2 cd = __ldg(d.cdesc + blockIdx.x);
+  const bool wvalid = wi < cd.y;
+  WDesc wd{0, 0, 0, 0, 0, 0xffff};
+  if (wvalid) wd = load_desc(d.wdesc, cd.x + wi);
+  const bool staged = wvalid && wd.soff != 0xffff && wd.D > 0;
+  const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
+  const bool pvalid = wvalid && (wd.heavy || lane < wd.np);
+  const size_t npl = (size_t)d.nPlPad;
+  // ---- solve-constant data: the bulk copies of this warp's slice go out first
+  T *my_stage = stage + (size_t)(staged ? wd.soff : 0) * 256;
+  int *my_cams = cstage + (size_t)(staged ? wd.soff : 0) * 32;
+  if (staged) {
+    if (lane == 0) {
+      mbar_init(bars + wi, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the async proxy must see the initialised barrier
+      const unsigned b_stream = (unsigned)wd.D * 256u * (unsigned)sizeof(T), b_cam = (unsigned)wd.D * 128u;
+      mbar_expect_tx(bars + wi, b_stream + b_cam);
+      bulk_g2s(my_stage, d.WJ + (size_t)wd.row0 * 256, b_stream, bars + wi);
+      bulk_g2s(my_cams, d.r_cam + (size_t)wd.row0 * 32, b_cam, bars + wi);
+    }
+    __syncwarp();
+  }
+  T X0 = T(0), X1 = T(0), X2 = T(0);
+  T hi[9], wv[3] = {T(0), T(0), T(0)};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) hi[k] = T(0);
+  if (pvalid) {
+    X0 = __ldg(d.XP + p); X1 = __ldg(d.XP + npl + p); X2 = __ldg(d.XP + 2 * npl + p);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInvP + k * npl + p);
+    if (MODE != SM_FULL) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wv[k] = __ldg(d.wP + k * npl + p);
+    }
+  }
+  if (check_active) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the bulk copies in flight target this CTA's shared memory: they must have landed before the CTA may exit
+    if (!d.st->active) { if (staged) mbar_wait(bars + wi, 0); return; }
+  }
+  if (MODE == SM_FULL && zero_set) {
+    const unsigned tot = (unsigned)NREP * 9u * (unsigned)d.nC;
+    for (unsigned i = blockIdx.x * ELL_THREADS + tid; i < tot; i += gridDim.x * ELL_THREADS) zero_set[i] = T(0);
+  }
+  if (!wvalid) return;
+  T *dst = MODE != SM_BACKSUB ? sout + (size_t)(blockIdx.x % NREP) * (9 * (size_t)d.nC) : nullptr;
+  if (staged) mbar_wait(bars + wi, 0);
+  // one row of the slice: camera index and the 8 stream values of this lane's slot
+  auto row_cam = [&](int r) -> int {
+    return staged ? my_cams[r * 32 + lane] : __ldg(d.r_cam + ((size_t)wd.row0 + r) * 32 + lane);
+  };
+  auto row_stream = [&](int r, T *sl) {
+    if (staged) {
+      const V *src = reinterpret_cast<const V *>(my_stage) + (size_t)r * 128 + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const V x = src[j * 32]; sl[2 * j] = x.x; sl[2 * j + 1] = x.y; }
+    } else {
+      load_stream<T, 8>(d.WJ, (size_t)wd.row0 + r, lane, sl);
+    }
+  };
+  // ---- phase 1
+  T t0 = T(0), t1 = T(0), t2 = T(0);
+#pragma unroll 2
+  for (int r = 0; r < wd.D; ++r) {
+    const int c = row_cam(r);
+    T sl[8];
+    row_stream(r, sl);
+    if (c >= 0) {
+      __align__(16) T g[CamPad<T>::N];
+      gather_cam<T, true>(xin, c, g);
+      T om[4];
+      if (INFO) load_info<T>(d.r_info, ((size_t)wd.row0 + r) * 32 + lane, om);
+      fact_first<T, INFO>(sl, g, X0, X1, X2, om, t0, t1, t2);
+    }
+  }
+  if (wd.heavy) { t0 = warp_sum<T>(t0); t1 = warp_sum<T>(t1); t2 = warp_sum<T>(t2); }
+  T u0 = hi[0] * t0 + hi[1] * t1 + hi[2] * t2;
+  T u1 = hi[3] * t0 + hi[4] * t1 + hi[5] * t2;
+  T u2 = hi[6] * t0 + hi[7] * t1 + hi[8] * t2;
+  if (MODE == SM_INIT) { u0 -= wv[0]; u1 -= wv[1]; u2 -= wv[2]; }
+  if (MODE == SM_BACKSUB) {
+    if (pvalid && (!wd.heavy || lane == 0)) {
+      d.dxl[3 * (size_t)p] = wv[0] - u0;
+      d.dxl[3 * (size_t)p + 1] = wv[1] - u1;
+      d.dxl[3 * (size_t)p + 2] = wv[2] - u2;
+    }
+    return;
+  }
+  // ---- phase 2
+  for (int r = 0; r < wd.D; ++r) {
+    const int c = row_cam(r);
+    T sl[8], o[9];
+    row_stream(r, sl);
+    if (c >= 0) {
+      T om[4];
+      if (INFO) load_info<T>(d.r_info, ((size_t)wd.row0 + r) * 32 + lane, om);
+      fact_second<T, INFO>(sl, u0, u1, u2, X0, X1, X2, om, o);
+    }
+    warp_scatter9<T>(sv, sc, o, c, dst);
   }
 }
 
@@ -545,7 +708,7 @@ int launches_of_linearize_ell() { return 5; }
 
 int ell_rc() {
   static int v = -1;
-  if (v < 0) { const char *e = getenv("BA_ELL_RC"); v = e ? atoi(e) : 2; }
+  if (v < 0) { const char *e = getenv("BA_ELL_RC"); v = e ? atoi(e) : 0; }
   return v;
 }
 
@@ -576,13 +739,12 @@ static cudaError_t launch_schur_ell_rc(const Dev<T> &d, const T *xin, T *sout, T
   if constexpr (STORE != ST_FACT) {
     return launch_schur_ell_v<T, STORE, MODE, INFO, 0>(d, xin, sout, zero_set, check_active, st);
   } else if constexpr (INFO || MODE != SM_FULL) {
-    return launch_schur_ell_v<T, STORE, MODE, INFO, 2>(d, xin, sout, zero_set, check_active, st);
+    return launch_schur_ell_v<T, STORE, MODE, INFO, 0>(d, xin, sout, zero_set, check_active, st);
   } else {
     switch (ell_rc()) {  // the hot flavour: how many rows stay in registers between the phases is a tuning knob (BA_ELL_RC)
-      case 0: return launch_schur_ell_v<T, STORE, MODE, INFO, 0>(d, xin, sout, zero_set, check_active, st);
+      case 2: return launch_schur_ell_v<T, STORE, MODE, INFO, 2>(d, xin, sout, zero_set, check_active, st);
       case 4: return launch_schur_ell_v<T, STORE, MODE, INFO, 4>(d, xin, sout, zero_set, check_active, st);
-      case 6: return launch_schur_ell_v<T, STORE, MODE, INFO, 6>(d, xin, sout, zero_set, check_active, st);
-      default: return launch_schur_ell_v<T, STORE, MODE, INFO, 2>(d, xin, sout, zero_set, check_active, st);
+      default: return launch_schur_ell_v<T, STORE, MODE, INFO, 0>(d, xin, sout, zero_set, check_active, st);
     }
   }
 }
@@ -603,10 +765,55 @@ static cudaError_t launch_schur_ell_m(const Dev<T> &d, int mode, const T *xin, T
   }
 }
 
+int ell_tma() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("BA_TMA"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+template <typename T, int MODE, bool INFO>
+static cudaError_t launch_schur_tma_v(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  auto kern = k_schur_tma<T, MODE, INFO>;
+  const size_t smem = schur_tma_smem<T>(d.tma_rows);
+  static bool prepared_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!prepared_dev[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tma_smem<T>(64));
+    if (e != cudaSuccess) return e;
+    prepared_dev[dev & 63] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(d.nCta);
+  cfg.blockDim = dim3(ELL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (check_active && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, d, xin, sout, zero_set, check_active);
+}
+
+template <typename T, int MODE>
+static cudaError_t launch_schur_tma_i(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  if (d.r_info) return launch_schur_tma_v<T, MODE, true>(d, xin, sout, zero_set, check_active, st);
+  return launch_schur_tma_v<T, MODE, false>(d, xin, sout, zero_set, check_active, st);
+}
+
 // d.store is the EFFECTIVE store of the current linearisation (ST_FACT or ST_J)
 template <typename T>
 cudaError_t launch_schur_ell(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
   if (d.nW == 0) return cudaSuccess;
+  if (d.store == ST_FACT && ell_tma()) {
+    switch (mode) {
+      case SM_FULL: return launch_schur_tma_i<T, SM_FULL>(d, xin, sout, zero_set, check_active, st);
+      case SM_INIT: return launch_schur_tma_i<T, SM_INIT>(d, xin, sout, zero_set, check_active, st);
+      case SM_BACKSUB: return launch_schur_tma_i<T, SM_BACKSUB>(d, xin, sout, zero_set, check_active, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (d.store == ST_FACT) return launch_schur_ell_m<T, ST_FACT>(d, mode, xin, sout, zero_set, check_active, st);
   return launch_schur_ell_m<T, ST_J>(d, mode, xin, sout, zero_set, check_active, st);
 }

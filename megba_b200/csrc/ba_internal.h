@@ -45,7 +45,10 @@ constexpr int NTRI = 45;       // upper triangle of a 9x9 block
 constexpr int NREP = 16;        // replicas of the camera-space scatter target (spreads REDs over L2 slices)
 constexpr int AUX_GRID = 296;   // 2 CTAs per SM for the small grid-stride kernels
 constexpr int ELL_HEAVY = 32;   // points with more observations than this get a warp of their own
-constexpr int ELL_WARPS = 8;    // warps (slices) per CTA of the ELL kernels
+#ifndef BA_ELL_WARPS
+#define BA_ELL_WARPS 4
+#endif
+constexpr int ELL_WARPS = BA_ELL_WARPS;  // warps (slices) per CTA of the ELL kernels
 constexpr int CAMC = 16;        // per-camera constants for the edge kernels: cam[9], c, a, b, a', b', small, pad
 constexpr int CAMT = 27;        // per-camera transform blocks of the factored operator: Jr[9], R[9], E[9]
 enum Store { ST_W = 1, ST_J = 2, ST_FACT = 3 };
@@ -87,8 +90,9 @@ struct Dev {
   const T *e_info;              // [slot][4] or nullptr
   const int *pt_slot;           // [nPl] first slot of the point
   // ELL static graph (ell != 0; the tile fields above are then unused)
-  int ell, store, nW, nRows, nPlPad;
-  const int4 *wdesc;            // per warp: {first row, rows D, first point (device order), kind | np << 8}
+  int ell, store, nW, nRows, nPlPad, nCta, tma_rows;
+  const int4 *wdesc;            // per warp: {first row, rows D, first point (device order), kind | np << 8 | stage row << 16}
+  const int2 *cdesc;            // CTAs of the TMA-staged edge pass: {first warp, warps}
   const int *r_cam;             // [nRows][32] camera of the slot, -1 = padding
   const T *r_obs;               // [nRows][32][2]
   const T *r_info;              // [nRows][32][4] or nullptr

@@ -113,7 +113,7 @@ def test_ell_layout_invariants(name, ws):
         row = 0
         next_pt = 0
         for w, (row0, D, pt0, kw) in enumerate(warp):
-            kind, npts = kw & 0xFF, kw >> 8
+            kind, npts = kw & 0xFF, (kw >> 8) & 0xFF
             assert row0 == row and pt0 == next_pt  # rows and points are consumed in order, without gaps
             if kind == 1:  # heavy point: lane = observation
                 assert w < L["n_heavy"] and npts == 1 and D == -(-ldeg[pt0] // 32)
