@@ -72,6 +72,9 @@ def parse():
     ap.add_argument("--implicit", action="store_true")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="auto", choices=["auto", "ell", "tile"],
+                    help="auto = the library default (ELL layout, factored operator stream); tile = round-1 W/J stream kernels")
+    ap.add_argument("--no-readme-mode", action="store_true", help="skip the README-parameter run reported beside the fixed-work line")
     return ap.parse_args()
 
 
@@ -306,10 +309,13 @@ def data_label(P):
 def bench_config(args, P):
     return {"workload": f"{P.label} ({P.nC} cameras, {P.nP} points, {P.nE} observations)",
             "compute_kind": "implicit" if args.implicit else "explicit",
+            "layout": getattr(args, "layout", "auto"),
             "lm": {"tau": LM_REGION, "epsilon1": -1e-300, "epsilon2": -1, "note": "negative: both stopping tests disabled, exactly `steps` iterations"},
             "pcg": {"iters_per_lm_iter": args.pcg_iters, "tol": 0, "refuse_ratio": "inf"},
             "parallelism": f"point-sharded edges x{args.gpus}, cameras replicated",
-            "l2": "working set per PCG iteration (>1 GB) exceeds the 126 MB L2; no explicit flush"}
+            "l2": ("working set per PCG iteration (> 0.4 GB per rank at 1 GPU) exceeds the 126 MB L2; no explicit flush"
+                   if P.nE * 70 / max(args.gpus, 1) > 126e6 else
+                   "working set fits the 126 MB L2: the PCG pass is L2-resident by nature of the problem size")}
 
 
 def run_ours(args, P, dtype):
@@ -328,8 +334,10 @@ def run_ours(args, P, dtype):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", local))
 
+    layout = {"auto": capi.LAYOUT_AUTO, "ell": capi.LAYOUT_ELL, "tile": capi.LAYOUT_TILE}[args.layout]
     S = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype=dtype, implicit=args.implicit, device=local,
-                    rank=rank, world_size=ws)
+                    rank=rank, world_size=ws, layout=layout)
+    tile = args.layout == "tile"
     if ws > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -390,13 +398,28 @@ def run_ours(args, P, dtype):
     k_ms = max_over_ranks(st["schur_apply_ms"] / max(st["schur_apply_timed"], 1))
     achieved = a_pcg / (k_ms * 1e-3) / 1e9
     traffic = None
+    kname = (("k_schur_edge_full" if tile else "k_schur_ell_fact_full") + ("_f64" if dtype == np.float64 else "_f32"))
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and ws == 1 and args.workload == WORKLOAD and not args.implicit:
         with open(tpath) as fh:
-            traffic = json.load(fh).get("k_schur_edge_full_f64" if dtype == np.float64 else "k_schur_edge_full_f32")
-    roofline = {"bound": "hbm", "kernel": "k_schur_edge<FULL> (S*p edge pass of one PCG iteration)",
+            traffic = json.load(fh).get(kname)
+    # SURVEY.md section 8d writes the per-observation figure for a kernel that streams the stored Hpl block
+    # (27 s + 4 bytes); the default kernel streams 8 s + 4.  Both denominators are reported.
+    its = np.dtype(dtype).itemsize
+    nE_l, nP_l = P.nE / ws, P.nP / ws
+    a_survey = nE_l * ((24 if args.implicit else 27) * its + 4) + nP_l * (9 * its + 4) + P.nC * 216 * its
+    roofline = {"bound": "hbm",
+                "kernel": ("k_schur_edge<FULL> (tile layout, W/J stream)" if tile else
+                           "k_schur_ell<FACT,FULL> (ELL layout, factored stream: S*p edge pass of one PCG iteration)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": a_pcg,
+                "bytes_per_observation": {"stream": (a_pcg - P.nC * 216 * its) / max(nE_l, 1),
+                                          "what": "this kernel's compulsory HBM bytes per observation incl. the per-point blocks (DESIGN.md section 3)"},
+                "survey_8d_equivalent": {"algorithmic_bytes_per_launch": a_survey, "achieved": a_survey / (k_ms * 1e-3) / 1e9,
+                                         "frac": a_survey / (k_ms * 1e-3) / 1e9 / peak,
+                                         "what": "SURVEY.md section 8d bytes (a kernel streaming the stored 9x3 Hpl block) / this kernel's time"},
+                "limiter": "LSU data pipe of the SM (l1tex__data_pipe_lsu_wavefronts ~73 % busy: gather of the camera vector, RED "
+                           "scatter and its shared-memory transposition), not DRAM; see profiles/README.md",
                 "avg_launch_ms": k_ms, "launches_timed": int(st["schur_apply_timed"]), "launches": st["schur_apply_calls"],
                 "pcg_cam_kernel_avg_ms": st["pcg_cam_ms"] / max(st["pcg_cam_timed"], 1),
                 "linearize": {"algorithmic_bytes": a_lin,
@@ -436,6 +459,30 @@ def run_ours(args, P, dtype):
            "d2h_bytes_per_step": bytes_x + 8, "ms_per_step": 1e3 * e2e_s / args.steps,
            "what": "set_params(H2D) + ba_lm_solve(max_iter=1) + get_params(D2H) per step", "final_cost": cost}
 
+    # ---------------- README-parameter mode (README.md:58): stopping rules on, reported beside the fixed-work line
+    readme = None
+    if not args.no_readme_mode:
+        rk = dict(initial_region=LM_REGION, eps1=1.0, eps2=1e-10, pcg_max_iter=100, pcg_tol=1e-1, pcg_refuse=1.0)
+        S.set_params_ptr(cam_in.data_ptr(), pt_in.data_ptr())
+        S.lm_solve(lm_max_iter=3, **rk)  # warm-up
+        S.set_params_ptr(cam_in.data_ptr(), pt_in.data_ptr())
+        S.reset_stats()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        tr = S.lm_solve(lm_max_iter=100, **rk)
+        r1.record(stream)
+        barrier()
+        r_ms = max_over_ranks(r0.elapsed_time(r1))
+        rst = S.stats()
+        n_lm = len(tr) - 1
+        readme = {"lm_iters": n_lm, "pcg_iters_total": rst["pcg_iters"], "ms_total": r_ms,
+                  "lm_iters_per_sec": n_lm / (r_ms * 1e-3), "pcg_iters_per_sec_overall": rst["pcg_iters"] / (r_ms * 1e-3),
+                  "accepted": sum(1 for t in tr[1:] if t["accepted"] == 1), "start_cost": tr[0]["cost"],
+                  "final_cost": tr[-1]["cost"], "launches": rst["launches"],
+                  "params": "max_iter 100, solver_max_iter 100, solver_tol 1e-1, solver_refuse_ratio 1, tau 1e4, epsilon1 1, "
+                            "epsilon2 1e-10 (README.md:58); stops by the reference's own rules"}
+
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
         arm = CpuArm(P, args.implicit, dtype)
@@ -464,7 +511,7 @@ def run_ours(args, P, dtype):
             "pcg_iters_per_sec": pcg_rate, "pcg_iters_timed": st["pcg_iters"],
             "accepted_steps": sum(1 for t in trace[1:] if t["accepted"] == 1),
             "wall_ms_per_step": 1e3 * wall / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "reference_gpu_solver": ref_gpu, "e2e": e2e,
+            "roofline": roofline, "readme_mode": readme, "cpu_baseline": cpu, "reference_gpu_solver": ref_gpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
             "final_cost": trace[-1]["cost"], "start_cost": trace[0]["cost"],
         }

@@ -336,6 +336,9 @@ struct Impl {
   bool linearized = false;
   double region = 1e3;
   int store_cfg = ST_W;  // configured operator stream; Dev::store is the one in effect for the current linearisation
+  // ba_lm_solve fuses the scalar kernels behind the big ones so that an LM iteration costs three host round trips
+  // (solve + step norms, trial evaluation, linearisation + gradient norm) instead of five
+  bool fuse_norms = false, fuse_ginf = false, norms_valid = false, ginf_valid = false;
   virtual ~Impl() {}
   int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -752,7 +755,13 @@ struct ImplT : Impl {
     BA_TRY(allreduce_T(d.Hpp, 90 * (size_t)g.nC));
     BA_TRY(allreduce_scal(S_COST, 1, ncclSum));
     if (timing) { ev_end(ev); ev_lin.push_back(ev); }
+    if (fuse_ginf) {  // LM loop: ||g||_inf of the new gradient travels with the cost (one round trip less)
+      BA_CUDA(launch_ginf<T>(d, stream));
+      stats.launches += 2;
+      BA_TRY(allreduce_scal(S_GINF, 1, ncclMax));
+    }
     BA_TRY(fetch_scalars());
+    ginf_valid = fuse_ginf;
     if (cost) *cost = h_scal[S_COST];
     // a camera in the small-angle branch (theta^2 <= eps) makes this linearisation stream the Jacobian instead
     if (g.ell) d.store = (store_cfg == ST_FACT && h_scal[S_ANY_SMALL] == 0.) ? ST_FACT : ST_J;
@@ -877,23 +886,31 @@ struct ImplT : Impl {
       if (pend.valid) BA_TRY(poll(pend));
       pend = Pending{slot, true};
     }
-    if (pend.valid && !finished) BA_TRY(poll(pend));
+    if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); }
+    // Back-substitution (and, inside the LM loop, the step norms) are enqueued BEHIND the PCG launches without waiting
+    // for them: launches past the end of the loop are no-ops, so one host round trip at the very end fetches the final
+    // PCG state and the scalars together.
+    BA_TRY(pad_cam(d.dxc));
+    BA_TRY(schur_edge(SM_BACKSUB, d.xpad, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
+    if (timing) { ev_end(ev_s); ev_solve.push_back(ev_s); }
+    if (fuse_norms) {
+      BA_CUDA(launch_norms<T>(d, stream));
+      stats.launches += 2;
+      BA_TRY(allreduce_scal(S_DX2_PT, 2, ncclSum));
+    }
     {
-      // final state (also covers max_iter <= 0 and the over-enqueued chunk)
+      // final state (also covers the over-enqueued chunk)
       BA_CUDA(cudaMemcpyAsync(&h_st[0], d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
-      BA_CUDA(cudaMemcpyAsync(h_scal + S_XCHG_ERR, d.scal + S_XCHG_ERR, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      BA_CUDA(cudaMemcpyAsync(h_scal, d.scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, stream));
       BA_CUDA(cudaStreamSynchronize(stream));
       if (h_scal[S_XCHG_ERR] != 0.) return fail(BA_ERR_NCCL, "peer-memory exchange timed out (a rank did not arrive)");
+      norms_valid = fuse_norms;
     }
-    if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); }
     // inactive edge launches return immediately; only executed iterations are counted
     stats.schur_apply_calls -= (launched - h_st[0].n);
     // launches issued after the loop ended returned immediately: keep only the samples of iterations that ran
     for (auto &e : loc_schur) if (e.second < h_st[0].n) ev_schur.push_back(e.first);
     for (auto &e : loc_cam) if (e.second < h_st[0].n) ev_cam.push_back(e.first);
-    BA_TRY(pad_cam(d.dxc));
-    BA_TRY(schur_edge(SM_BACKSUB, d.xpad, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
-    if (timing) { ev_end(ev_s); ev_solve.push_back(ev_s); }
     stats.pcg_iters += h_st[0].n;
     if (iters) *iters = h_st[0].n;
     if (done) *done = h_st[0].done;
@@ -902,10 +919,13 @@ struct ImplT : Impl {
 
   int step_norms(double *dxn, double *xn) override {
     BA_CUDA(cudaSetDevice(opt.device));
-    BA_CUDA(launch_norms<T>(d, stream));
-    stats.launches += 2;
-    BA_TRY(allreduce_scal(S_DX2_PT, 2, ncclSum));
-    BA_TRY(fetch_scalars());
+    if (!norms_valid) {  // otherwise ba_solve computed and fetched them already (LM loop)
+      BA_CUDA(launch_norms<T>(d, stream));
+      stats.launches += 2;
+      BA_TRY(allreduce_scal(S_DX2_PT, 2, ncclSum));
+      BA_TRY(fetch_scalars());
+    }
+    norms_valid = false;
     if (dxn) *dxn = std::sqrt(h_scal[S_DX2_PT] + h_scal[S_DX2_CAM]);
     if (xn) *xn = std::sqrt(h_scal[S_X2_PT] + h_scal[S_X2_CAM]);
     return BA_OK;
@@ -948,10 +968,13 @@ struct ImplT : Impl {
 
   int grad_inf(double *gi) override {
     BA_CUDA(cudaSetDevice(opt.device));
-    BA_CUDA(launch_ginf<T>(d, stream));
-    stats.launches += 2;
-    BA_TRY(allreduce_scal(S_GINF, 1, ncclMax));
-    BA_TRY(fetch_scalars());
+    if (!ginf_valid) {
+      BA_CUDA(launch_ginf<T>(d, stream));
+      stats.launches += 2;
+      BA_TRY(allreduce_scal(S_GINF, 1, ncclMax));
+      BA_TRY(fetch_scalars());
+    }
+    ginf_valid = false;
     if (gi) *gi = h_scal[S_GINF];
     return BA_OK;
   }
@@ -1345,6 +1368,11 @@ int ba_lm_solve(ba_solver *s, const ba_lm_options *lm, const ba_pcg_options *pcg
   };
   const bool talk = verbose && m->opt.rank == 0;
   double F_new = 0., F = 0.;
+  struct Fuse {  // scoped: the step-by-step entry points keep their one-call-one-result behaviour
+    ba::Impl *m;
+    explicit Fuse(ba::Impl *mm) : m(mm) { m->fuse_norms = m->fuse_ginf = true; }
+    ~Fuse() { m->fuse_norms = m->fuse_ginf = m->norms_valid = m->ginf_valid = false; }
+  } fuse(m);
   BA_TRY(m->linearize(&F_new));                                               // :145-148
   double region = lm->initial_region;                                         // lm_algo.cpp:15
   if (talk) printf("Start with error: %g, log error: %g, elapsed %lld ms\n", F_new / 2, std::log10(F_new / 2), (long long)elapsed());
