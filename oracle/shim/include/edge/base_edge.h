@@ -17,6 +17,7 @@ class EdgeVector {
   std::vector<PositionContainer> positionContainers;
   JVD<T> jetInformation;
   void buildLinearSystemCUDA(const JVD<T> &jetEstimation, const BaseLinearSystem<T> &linearSystem) const;
+  void buildImplicitLinearSystemCUDA(const JVD<T> &jetEstimation, const BaseLinearSystem<T> &linearSystem) const;
   // what LMAlgo::solveCUDA calls (base_edge.h:99-152); forward/backup/rollback/update are provided by the driver
   const std::vector<PositionContainer> &getPositionContainers() const { return positionContainers; }
   JVD<T> forward() const;

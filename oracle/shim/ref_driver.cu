@@ -33,11 +33,55 @@
 #include "resource/handle_manager.h"
 #include "resource/memory_pool.h"
 #include "solver/schur_pcg_solver.h"
+#include "linear_system/implicit_schur_LM_linear_system.h"
+#include "solver/implicit_schur_pcg_solver.h"
 
 namespace MegBA {
 const ProblemOption *MemoryPool::_problemOption = nullptr;
-void MemoryPool::allocateNormal(void **ptr, size_t size, int rank) { cudaSetDevice(rank); cudaMalloc(ptr, size ? size : 8); }
-void MemoryPool::deallocateNormal(void *ptr, int rank) { cudaSetDevice(rank); cudaFree(ptr); }
+// MemoryPool::allocateNormal / deallocateNormal: the reference serves these from a pre-reserved stack
+// (src/resource/memory_pool.cu); a cudaMalloc / cudaFree per call would charge its solver and LM loop with driver calls it
+// does not make.  Same discipline here: one slab, bump allocation, frees pop the stack (out-of-order frees are deferred).
+namespace {
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, top = 0;
+  struct Blk { size_t off, size; bool freed; };
+  std::vector<Blk> blks;
+} g_arena;
+}  // namespace
+void MemoryPool::allocateNormal(void **ptr, size_t size, int rank) {
+  cudaSetDevice(rank);
+  if (!g_arena.base) {
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    g_arena.cap = std::min<size_t>(fr / 4, (size_t)8 << 30);
+    if (cudaMalloc(&g_arena.base, g_arena.cap) != cudaSuccess) { g_arena.base = nullptr; g_arena.cap = 0; cudaGetLastError(); }
+  }
+  const size_t need = ((size ? size : 8) + 255) / 256 * 256;
+  if (g_arena.base && g_arena.top + need <= g_arena.cap) {
+    *ptr = g_arena.base + g_arena.top;
+    g_arena.blks.push_back({g_arena.top, need, false});
+    g_arena.top += need;
+    // Blocks are handed out zeroed: the implicit solver's MakeV accumulates into a pool buffer with atomics without
+    // clearing it first (implicit_schur_pcg_solver.cu:500-528), i.e. upstream relies on what a
+    // fresh pool happens to contain.  Zero is the intended content; a recycled arena block would otherwise hold the
+    // previous solve's data.
+    cudaMemsetAsync(*ptr, 0, need, nullptr);
+  } else {
+    cudaMalloc(ptr, need);  // arena exhausted: fall back to the driver
+  }
+}
+void MemoryPool::deallocateNormal(void *ptr, int rank) {
+  cudaSetDevice(rank);
+  char *p = (char *)ptr;
+  if (g_arena.base && p >= g_arena.base && p < g_arena.base + g_arena.cap) {
+    for (auto it = g_arena.blks.rbegin(); it != g_arena.blks.rend(); ++it)
+      if (g_arena.base + it->off == p) { it->freed = true; break; }
+    while (!g_arena.blks.empty() && g_arena.blks.back().freed) { g_arena.top = g_arena.blks.back().off; g_arena.blks.pop_back(); }
+  } else {
+    cudaFree(ptr);
+  }
+}
 std::vector<cublasHandle_t> HandleManager::cublasHandle{};
 std::vector<cusparseHandle_t> HandleManager::cusparseHandle{};
 }  // namespace MegBA
@@ -250,6 +294,93 @@ int solve_impl(int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx, const
   cudaFree(ls.g[0]); cudaFree(ls.deltaXPtr[0]);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+
+// a3' / a7 implicit: EdgeVector::buildImplicitLinearSystemCUDA (src/edge/build_implicit_linear_system.cu:208-322, kernel
+// makeHppHllSchur :65-111) and ImplicitSchurPCGSolver::solve (src/solver/implicit_schur_pcg_solver.cu:661-720: block
+// inverses, MakeV :476-549, the matrix-free PCG :181-473 with implicitETMulx / implicitEMulx :21-90, SolveW :552-618).
+template <typename T>
+struct JetPair {  // J / r as two JetVectors (one per residual row), slab layout [grad 12 x nE | res nE]
+  JVD<T> jet;
+  std::vector<T *> slabs;
+  JetPair(int64_t nE, const T *r, const T *J) {
+    jet.resize(2, 1);
+    for (int row = 0; row < 2; ++row) {
+      std::vector<T> h(13 * (size_t)nE);
+      for (int64_t e = 0; e < nE; ++e) {
+        for (int k = 0; k < 12; ++k) h[(size_t)k * nE + e] = J[24 * e + 12 * row + k];
+        h[(size_t)12 * nE + e] = r ? r[2 * e + row] : T(0);
+      }
+      T *d = dev_copy(h);
+      slabs.push_back(d);
+      jet(row).bind(12, {(size_t)nE}, {d + (size_t)12 * nE}, {d});
+    }
+  }
+  ~JetPair() { for (auto *s : slabs) cudaFree(s); }
+};
+
+template <typename T>
+int build_implicit_impl(int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx, const int32_t *pt_idx, const T *r, const T *J,
+                        T *Hpp, T *Hll, T *g) {
+  ProblemOption opt; opt.deviceUsed = {0}; opt.N = 12; opt.nItem = nE;
+  MemoryPool::resetPool(&opt);
+  cudaSetDevice(0);
+  JetPair<T> jp(nE, r, J);
+  EdgeVector<T> edges(opt);
+  edges.positionContainers.resize(1);
+  std::vector<int> ac(cam_idx, cam_idx + nE), ap(pt_idx, pt_idx + nE);
+  int *dac = dev_copy(ac), *dap = dev_copy(ap);
+  edges.positionContainers[0].absolutePosition = {dac, dap};
+  ImplicitSchurLMLinearSystem<T> ls(opt);
+  ls.dim = {9, 3}; ls.num = {(int)nC, (int)nP};
+  ls.implicitEquationContainers.resize(1);
+  auto &ec = ls.implicitEquationContainers[0];
+  ec.nnz = {(size_t)81 * nC, (size_t)9 * nP};
+  for (int k = 0; k < 2; ++k) ec.csrVal[k] = dev_alloc<T>(ec.nnz[k]);
+  ls.g = {dev_alloc<T>(9 * nC + 3 * nP)};
+  edges.buildImplicitLinearSystemCUDA(jp.jet, ls);
+  cudaDeviceSynchronize();
+  cudaMemcpy(Hpp, ec.csrVal[0], sizeof(T) * 81 * nC, cudaMemcpyDeviceToHost);
+  cudaMemcpy(Hll, ec.csrVal[1], sizeof(T) * 9 * nP, cudaMemcpyDeviceToHost);
+  cudaMemcpy(g, ls.g[0], sizeof(T) * (9 * nC + 3 * nP), cudaMemcpyDeviceToHost);
+  cudaFree(ec.csrVal[0]); cudaFree(ec.csrVal[1]); cudaFree(ls.g[0]); cudaFree(dac); cudaFree(dap);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <typename T>
+int solve_implicit_impl(int64_t nC, int64_t nP, int64_t nE, const int32_t *cam_idx, const int32_t *pt_idx, const T *HppD, const T *HllD,
+                        const T *J, const T *g, T *dx, int max_iter, double tol, double refuse) {
+  ProblemOption opt; opt.deviceUsed = {0}; opt.N = 12; opt.nItem = nE;
+  MemoryPool::resetPool(&opt);
+  cudaSetDevice(0);
+  ensure_handles();
+  JetPair<T> jp(nE, nullptr, J);
+  EdgeVector<T> edges(opt);
+  edges.positionContainers.resize(1);
+  std::vector<int> ac(cam_idx, cam_idx + nE), ap(pt_idx, pt_idx + nE);
+  int *dac = dev_copy(ac), *dap = dev_copy(ap);
+  edges.positionContainers[0].absolutePosition = {dac, dap};
+  ImplicitSchurLMLinearSystem<T> ls(opt);
+  ls.dim = {9, 3}; ls.num = {(int)nC, (int)nP};
+  ls.implicitEquationContainers.resize(1);
+  auto &ec = ls.implicitEquationContainers[0];
+  ec.nnz = {(size_t)81 * nC, (size_t)9 * nP};
+  ec.csrVal[0] = dev_alloc<T>(81 * nC); ec.csrVal[1] = dev_alloc<T>(9 * nP);
+  cudaMemcpy(ec.csrVal[0], HppD, sizeof(T) * 81 * nC, cudaMemcpyHostToDevice);
+  cudaMemcpy(ec.csrVal[1], HllD, sizeof(T) * 9 * nP, cudaMemcpyHostToDevice);
+  const size_t nX = 9 * nC + 3 * nP;
+  ls.g = {dev_alloc<T>(nX)};
+  ls.deltaXPtr = {dev_alloc<T>(nX)};
+  cudaMemcpy(ls.g[0], g, sizeof(T) * nX, cudaMemcpyHostToDevice);
+  cudaMemcpy(ls.deltaXPtr[0], dx, sizeof(T) * nX, cudaMemcpyHostToDevice);
+  SolverOption so;
+  so.solverOptionPCG.maxIter = max_iter; so.solverOptionPCG.tol = tol; so.solverOptionPCG.refuseRatio = refuse;
+  ImplicitSchurPCGSolver<T> solver(opt, so);
+  solver.solve(ls, edges, jp.jet);
+  cudaDeviceSynchronize();
+  cudaMemcpy(dx, ls.deltaXPtr[0], sizeof(T) * nX, cudaMemcpyDeviceToHost);
+  cudaFree(ec.csrVal[0]); cudaFree(ec.csrVal[1]); cudaFree(ls.g[0]); cudaFree(ls.deltaXPtr[0]); cudaFree(dac); cudaFree(dap);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 }  // namespace
 
 namespace MegBA {
@@ -374,5 +505,9 @@ int ref_solve_f64(int64_t nC, int64_t nP, int64_t nE, const int32_t *ci, const i
 // same as ref_solve_f64, additionally reports the device time of SchurPCGSolver::solve (used by bench.py to quote the
 // reference's own cuSPARSE/cuBLAS solver on the same GPU and problem)
 int ref_solve_timed_f64(int64_t nC, int64_t nP, int64_t nE, const int32_t *ci, const int32_t *pi, const double *HppD, const double *HllD, const double *W, const double *g, double *dx, int max_iter, double tol, double refuse, double *ms) { return solve_impl<double>(nC, nP, nE, ci, pi, HppD, HllD, W, g, dx, max_iter, tol, refuse, ms); }
+int ref_build_implicit_f64(int64_t nC, int64_t nP, int64_t nE, const int32_t *ci, const int32_t *pi, const double *r, const double *J, double *Hpp, double *Hll, double *g) { return build_implicit_impl<double>(nC, nP, nE, ci, pi, r, J, Hpp, Hll, g); }
+int ref_build_implicit_f32(int64_t nC, int64_t nP, int64_t nE, const int32_t *ci, const int32_t *pi, const float *r, const float *J, float *Hpp, float *Hll, float *g) { return build_implicit_impl<float>(nC, nP, nE, ci, pi, r, J, Hpp, Hll, g); }
+int ref_solve_implicit_f64(int64_t nC, int64_t nP, int64_t nE, const int32_t *ci, const int32_t *pi, const double *HppD, const double *HllD, const double *J, const double *g, double *dx, int max_iter, double tol, double refuse) { return solve_implicit_impl<double>(nC, nP, nE, ci, pi, HppD, HllD, J, g, dx, max_iter, tol, refuse); }
+int ref_solve_implicit_f32(int64_t nC, int64_t nP, int64_t nE, const int32_t *ci, const int32_t *pi, const float *HppD, const float *HllD, const float *J, const float *g, float *dx, int max_iter, double tol, double refuse) { return solve_implicit_impl<float>(nC, nP, nE, ci, pi, HppD, HllD, J, g, dx, max_iter, tol, refuse); }
 int ref_solve_f32(int64_t nC, int64_t nP, int64_t nE, const int32_t *ci, const int32_t *pi, const float *HppD, const float *HllD, const float *W, const float *g, float *dx, int max_iter, double tol, double refuse) { return solve_impl<float>(nC, nP, nE, ci, pi, HppD, HllD, W, g, dx, max_iter, tol, refuse); }
 }

@@ -322,6 +322,43 @@ def test_full_size_venice_properties_and_parity():
     assert rel_fro(S.read(capi.BUF_DX), dx0) <= 1e-8
 
 
+@pytest.mark.parametrize("workload,dtype,implicit", [("ladybug-49", np.float64, False),
+                                                     ("trafalgar-257", np.float64, False),
+                                                     ("venice-1778", np.float64, True),
+                                                     ("final-13682", np.float32, False)])
+def test_full_size_baseline_configs(workload, dtype, implicit):
+    """The other BASELINE.json configurations at their full sizes (synthetic problems of the BAL shapes): configs[0]
+    Ladybug-49 fp64, configs[1] Trafalgar-257 fp64, configs[4] Venice-1778 matrix-free fp64 and configs[3]
+    Final-13682 fp32 (the size that takes the cooperative-grid camera kernel): linearisation + 8 fixed PCG iterations
+    against the oracle, plus operator symmetry / linearity."""
+    P = make_named(workload)
+    S, O = _pair(P, dtype, implicit=implicit)
+    t = TOL[np.dtype(dtype)]
+    cost = S.linearize()
+    r, J = O.forward(P.cam, P.pt)
+    Hpp, Hll, W, g = O.build(r, J, explicit=not implicit)
+    assert abs(cost - O.cost(r)) <= t["cost"] * O.cost(r)
+    assert rel_fro(S.read(capi.BUF_HPP), Hpp) <= t["H"]
+    assert rel_fro(S.read(capi.BUF_HLL), Hll) <= t["H"]
+    assert rel_fro(S.read(capi.BUF_G), g) <= t["H"]
+    region = 1e4
+    S.process_diag(region)
+    rng = np.random.default_rng(0)
+    p1, p2 = rng.normal(size=9 * P.nC), rng.normal(size=9 * P.nC)
+    q1, q2 = S.schur_apply(p1).astype(np.float64), S.schur_apply(p2).astype(np.float64)
+    eps = 1e-9 if dtype == np.float64 else 5e-4
+    assert abs(p2 @ q1 - p1 @ q2) <= eps * abs(p1 @ q1)
+    assert p1 @ q1 > 0 and p2 @ q2 > 0
+    assert rel_fro(S.schur_apply(p1 + 3.0 * p2), q1 + 3.0 * q2) <= eps
+    HppD, _ = O.process_diag(Hpp, region)
+    HllD, _ = O.process_diag(Hll, region)
+    del r
+    it, _ = S.solve(max_iter=8, tol=0.0, refuse_ratio=1e300)
+    dx0, it0, _, _ = O.schur_pcg(HppD, HllD, W, J if implicit else None, g, np.zeros(9 * P.nC + 3 * P.nP), 8, 0.0, 1e300)
+    assert it == it0 == 8
+    assert rel_fro(S.read(capi.BUF_DX), dx0) <= t["dx"]
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_many_cameras_cooperative_grid_pcg_kernel(dtype):
     """3000 cameras do not fit one 16-CTA cluster at <= 2 rows per thread: the camera-space PCG kernel runs as a
