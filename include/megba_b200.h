@@ -182,6 +182,11 @@ const char *ba_last_error(const ba_solver *s);
 int ba_comm_unique_id(void *id128);
 int ba_comm_init(ba_solver *s, const void *id128);
 
+/* All ranks are solvers of THIS process (one host thread per rank afterwards, as with ba_comm_init): no NCCL; the
+ * ranks may share a device, so the partition count can differ from the device count (e.g. 4 shards on one GPU).
+ * solvers[r] must have been created with rank = r, world_size = n.  Call once, from one thread.                  */
+int ba_comm_init_local(ba_solver **solvers, int32_t n);
+
 /* BaseProblem::setAbsolutePosition (H2D of x, src/problem/base_problem.cpp:217-247)
  * and writeBack (:250-272).  cam[nC][9], pt[nP][3].                                */
 int ba_set_params(ba_solver *s, const void *cam, const void *pt);

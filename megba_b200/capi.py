@@ -23,7 +23,7 @@ BUF_HPP, BUF_HLL, BUF_W, BUF_J, BUF_G, BUF_DX = range(6)
 # every symbol include/megba_b200.h declares (tests check the export list against the header)
 SYMBOLS = [
     "ba_abi_version", "ba_partition_points", "ba_create", "ba_destroy", "ba_last_error",
-    "ba_comm_unique_id", "ba_comm_init", "ba_set_params", "ba_get_params", "ba_set_information",
+    "ba_comm_unique_id", "ba_comm_init", "ba_comm_init_local", "ba_set_params", "ba_get_params", "ba_set_information",
     "ba_linearize", "ba_process_diag", "ba_solve", "ba_step_norms", "ba_eval_trial",
     "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
     "ba_eval_edges", "ba_schur_apply", "ba_set_timing", "ba_reset_stats", "ba_get_stats",
@@ -219,6 +219,14 @@ class Solver:
         if rc != 0:
             raise RuntimeError(f"ba_comm_unique_id failed: {rc}")
         return buf.raw
+
+    @staticmethod
+    def comm_init_local(solvers):
+        """In-process communicator over `solvers` (rank r = solvers[r]); afterwards drive each solver from its own thread."""
+        arr = (C.c_void_p * len(solvers))(*[s.h.value for s in solvers])
+        rc = load().ba_comm_init_local(arr, len(solvers))
+        if rc != 0:
+            raise RuntimeError(f"ba_comm_init_local failed: {rc}")
 
     def comm_init(self, uid: bytes):
         self._chk(self.L.ba_comm_init(self.h, C.c_char_p(uid)), "ba_comm_init")

@@ -7,13 +7,17 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/megba_b200.h"
@@ -40,6 +44,28 @@ namespace ba {
 template <typename T> struct NcclType;
 template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
 template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
+
+// In-process communicator (ba_comm_init_local): the ranks are solvers of ONE process, one host thread each, on the same
+// or on different devices -- NCCL cannot put two ranks on one device, and a partition count different from the device
+// count (SURVEY.md section 4 vi) needs exactly that.  Collectives outside the PCG loop rendezvous on a host barrier and
+// sum the ranks' buffers with a small kernel over (peer) device pointers, in rank order; the per-iteration exchange is
+// the same fused peer-memory exchange as with NCCL ranks.
+struct LocalComm {
+  int n = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long long gen = 0;
+  const void *ptr[8] = {};
+  int dev[8] = {};
+  int okflag[8] = {};
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const unsigned long long g = gen;
+    if (++arrived == n) { arrived = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+};
 
 // Host-side, dtype-independent result of graph preprocessing.
 struct HostGraph {
@@ -330,6 +356,7 @@ struct Impl {
   cudaStream_t stream = nullptr;
   ncclComm_t comm = nullptr;
   bool comm_ready = false;
+  std::shared_ptr<LocalComm> local;  // in-process communicator instead of NCCL
   bool timing = false;
   int timing_stride = 1;  // per-launch events are recorded for every timing_stride-th PCG iteration
   ba_stats stats{};
@@ -379,6 +406,7 @@ struct ImplT : Impl {
   size_t arena_bytes = 0;
   T *e_info_dev = nullptr, *cm_info_dev = nullptr;
   T *pt_full = nullptr;  // [3 nP] gather buffer, world_size > 1 only
+  void *coll_scratch = nullptr;  // result buffer of the in-process allreduce (>= 90 nC scalars)
   // ELL layout
   int *perm_dev = nullptr; // [nPl] device position -> local point
   T *pt_nat = nullptr;     // [3 nPl] staging in the caller's point order
@@ -405,6 +433,7 @@ struct ImplT : Impl {
     if (cm_info_dev) cudaFree(cm_info_dev);
     if (r_info_dev) cudaFree(r_info_dev);
     if (pt_full) cudaFree(pt_full);
+    if (coll_scratch) cudaFree(coll_scratch);
     for (auto *q : ipc_opened) if (q) cudaIpcCloseMemHandle(q);
     if (xchg) cudaFree(xchg);
     if (h_scal) cudaFreeHost(h_scal);
@@ -449,14 +478,32 @@ struct ImplT : Impl {
   }
 
   // ---- collectives ----------------------------------------------------------
+  // in-process flavour: every rank sums all ranks' buffers (rank order) into its own scratch, then copies back
+  template <typename U>
+  int local_allreduce(U *p, size_t n, int op) {
+    BA_CUDA(cudaStreamSynchronize(stream));
+    local->ptr[opt.rank] = p;
+    local->barrier();
+    const void *srcs[8];
+    for (int r = 0; r < 8; ++r) srcs[r] = r < local->n ? local->ptr[r] : nullptr;
+    U *tmp = reinterpret_cast<U *>(coll_scratch);
+    BA_CUDA(launch_sum_ranks<U>(tmp, srcs, local->n, n, op, stream));
+    stats.launches += 1;
+    BA_CUDA(cudaStreamSynchronize(stream));
+    local->barrier();  // everybody has read every source
+    BA_CUDA(cudaMemcpyAsync(p, tmp, sizeof(U) * n, cudaMemcpyDeviceToDevice, stream));
+    return BA_OK;
+  }
   int allreduce_T(T *p, size_t n) {
     if (opt.world_size == 1) return BA_OK;
+    if (local) return local_allreduce<T>(p, n, 0);
     if (!comm_ready) return fail(BA_ERR_STATE, "world_size > 1 but ba_comm_init was not called");
     BA_NCCL(ncclAllReduce(p, p, n, NcclType<T>::v, ncclSum, comm, stream));
     return BA_OK;
   }
   int allreduce_scal(int first, int n, ncclRedOp_t op) {
     if (opt.world_size == 1) return BA_OK;
+    if (local) return local_allreduce<double>(d.scal + first, (size_t)n, op == ncclMax ? 1 : op == ncclMin ? 2 : 0);
     if (!comm_ready) return fail(BA_ERR_STATE, "world_size > 1 but ba_comm_init was not called");
     BA_NCCL(ncclAllReduce(d.scal + first, d.scal + first, n, ncclDouble, op, comm, stream));
     return BA_OK;
@@ -467,36 +514,50 @@ struct ImplT : Impl {
     return BA_OK;
   }
 
-  // Maps every rank's exchange buffer into this rank's address space (CUDA IPC across processes, plain peer
-  // access between threads of one process).  Any failure leaves p2p = false and the NCCL path in use.
+  // Maps every rank's inbox (see PeerExchange) into this rank's address space: CUDA IPC across processes, plain
+  // (peer) pointers between solvers of one process.  Any failure leaves p2p = false and the fold + allreduce path in use.
   int setup_p2p() override {
-    if (opt.world_size == 1 || opt.world_size > 8 || !comm_ready) return BA_OK;
+    if (opt.world_size == 1 || opt.world_size > 8 || (!comm_ready && !local)) return BA_OK;
     BA_CUDA(cudaSetDevice(opt.device));
-    const size_t n9 = 9 * (size_t)g.nC, bytes = sizeof(T) * 4 * n9, off = (bytes + 255) / 256 * 256;
+    const size_t n9 = 9 * (size_t)g.nC, bytes = sizeof(T) * 2 * (size_t)opt.world_size * 2 * n9, off = (bytes + 255) / 256 * 256;
     struct Info { cudaIpcMemHandle_t h; long long pid; unsigned long long ptr; int dev, ok; char pad[128 - sizeof(cudaIpcMemHandle_t) - 24]; };
     static_assert(sizeof(Info) == 128, "Info is one 128-byte record");
     Info mine{};
     int ok = 1;
     if (cudaMalloc(&xchg, off + 256) != cudaSuccess) { cudaGetLastError(); xchg = nullptr; ok = 0; }
     if (ok && cudaMemset(xchg, 0, off + 256) != cudaSuccess) ok = 0;
-    if (ok && cudaIpcGetMemHandle(&mine.h, xchg) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    if (ok && !local && cudaIpcGetMemHandle(&mine.h, xchg) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     mine.pid = (long long)getpid(); mine.ptr = (unsigned long long)xchg; mine.dev = opt.device; mine.ok = ok;
-    char *scratch = reinterpret_cast<char *>(d.partials);  // >= 8 * 128 bytes
     std::vector<Info> all(opt.world_size);
-    BA_CUDA(cudaMemcpyAsync(scratch + 128 * opt.rank, &mine, 128, cudaMemcpyHostToDevice, stream));
-    BA_NCCL(ncclAllGather(scratch + 128 * opt.rank, scratch, 128, ncclChar, comm, stream));
-    BA_CUDA(cudaMemcpyAsync(all.data(), scratch, 128 * opt.world_size, cudaMemcpyDeviceToHost, stream));
-    BA_CUDA(cudaStreamSynchronize(stream));
+    if (local) {
+      static std::mutex info_mu;
+      static std::vector<Info> board(8);
+      { std::lock_guard<std::mutex> lk(info_mu); board[opt.rank] = mine; }
+      local->barrier();
+      { std::lock_guard<std::mutex> lk(info_mu); for (int r = 0; r < opt.world_size; ++r) all[r] = board[r]; }
+      local->barrier();
+    } else {
+      char *scratch = reinterpret_cast<char *>(d.partials);  // >= 8 * 128 bytes
+      BA_CUDA(cudaMemcpyAsync(scratch + 128 * opt.rank, &mine, 128, cudaMemcpyHostToDevice, stream));
+      BA_NCCL(ncclAllGather(scratch + 128 * opt.rank, scratch, 128, ncclChar, comm, stream));
+      BA_CUDA(cudaMemcpyAsync(all.data(), scratch, 128 * opt.world_size, cudaMemcpyDeviceToHost, stream));
+      BA_CUDA(cudaStreamSynchronize(stream));
+    }
     px = PeerExchange{};
+    bool shared_dev = false;
     for (int r = 0; r < opt.world_size; ++r) {
       void *ptr = nullptr;
       if (!all[r].ok) { ok = 0; continue; }
       if (r == opt.rank) {
         ptr = xchg;
-      } else if (all[r].pid == mine.pid) {  // another host thread of this process: direct peer access
-        cudaError_t e = cudaDeviceEnablePeerAccess(all[r].dev, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
-        cudaGetLastError();
+      } else if (all[r].pid == mine.pid) {  // another solver of this process: direct (peer) pointers
+        if (all[r].dev != opt.device) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(all[r].dev, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+          cudaGetLastError();
+        } else {
+          shared_dev = true;
+        }
         ptr = (void *)all[r].ptr;
       } else if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
         ipc_opened[r] = ptr;
@@ -507,10 +568,11 @@ struct ImplT : Impl {
       px.data[r] = ptr;
       px.flag[r] = ptr ? reinterpret_cast<unsigned long long *>((char *)ptr + off) : nullptr;
     }
+    d.no_pdl = shared_dev ? 1 : 0;
     // every rank must take the same path: agree on min(ok)
     double okd = ok;
     BA_CUDA(cudaMemcpyAsync(d.scal + S_XCHG_ERR, &okd, sizeof(double), cudaMemcpyHostToDevice, stream));
-    BA_NCCL(ncclAllReduce(d.scal + S_XCHG_ERR, d.scal + S_XCHG_ERR, 1, ncclDouble, ncclMin, comm, stream));
+    BA_TRY(allreduce_scal(S_XCHG_ERR, 1, ncclMin));
     BA_CUDA(cudaMemcpyAsync(&okd, d.scal + S_XCHG_ERR, sizeof(double), cudaMemcpyDeviceToHost, stream));
     BA_CUDA(cudaMemsetAsync(d.scal + S_XCHG_ERR, 0, sizeof(double), stream));
     BA_CUDA(cudaStreamSynchronize(stream));
@@ -613,7 +675,10 @@ struct ImplT : Impl {
     BA_CUDA(cudaHostAlloc(&h_st, 2 * sizeof(PcgState), cudaHostAllocDefault));
     BA_CUDA(cudaEventCreateWithFlags(&st_event[0], cudaEventDisableTiming));
     BA_CUDA(cudaEventCreateWithFlags(&st_event[1], cudaEventDisableTiming));
-    if (opt.world_size > 1) BA_CUDA(cudaMalloc(&pt_full, sizeof(T) * 3 * g.nP));
+    if (opt.world_size > 1) {
+      BA_CUDA(cudaMalloc(&pt_full, sizeof(T) * 3 * g.nP));
+      BA_CUDA(cudaMalloc(&coll_scratch, std::max<size_t>(sizeof(T) * 90 * nC, sizeof(double) * S_COUNT)));
+    }
     BA_CUDA(cudaStreamSynchronize(stream));
     // free the big host staging vectors that are no longer needed
     std::vector<int>().swap(g.e_cam);
@@ -660,6 +725,18 @@ struct ImplT : Impl {
       BA_CUDA(cudaMemcpyAsync(pt, own, sizeof(T) * 3 * g.nP, cudaMemcpyDeviceToHost, stream));
     } else {
       // every rank owns a contiguous point range: an all-gather with per-rank counts = one broadcast per rank, grouped
+      if (local) {
+        BA_CUDA(cudaStreamSynchronize(stream));
+        local->ptr[opt.rank] = own;
+        local->barrier();
+        for (int r = 0; r < opt.world_size; ++r) {
+          const size_t cnt = 3 * (size_t)(g.cuts[r + 1] - g.cuts[r]);
+          if (cnt) BA_CUDA(cudaMemcpyAsync(pt + 3 * g.cuts[r], local->ptr[r], sizeof(T) * cnt, cudaMemcpyDeviceToHost, stream));
+        }
+        BA_CUDA(cudaStreamSynchronize(stream));
+        local->barrier();
+        return BA_OK;
+      }
       if (!comm_ready) return fail(BA_ERR_STATE, "world_size > 1 but ba_comm_init was not called");
       if (g.nPl)
         BA_CUDA(cudaMemcpyAsync(pt_full + 3 * g.pt_begin, own, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
@@ -1317,6 +1394,28 @@ int ba_comm_init(ba_solver *s, const void *id128) {
   if (r != ncclSuccess) return m->fail(BA_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
   m->comm_ready = true;
   return m->setup_p2p();
+}
+
+int ba_comm_init_local(ba_solver **solvers, int32_t n) {
+  if (!solvers || n < 1 || n > 8) return BA_ERR_ARG;
+  auto lc = std::make_shared<ba::LocalComm>();
+  lc->n = n;
+  for (int r = 0; r < n; ++r) {
+    if (!solvers[r]) return BA_ERR_ARG;
+    ba::Impl *m = solvers[r]->impl.get();
+    if (m->opt.world_size != n || m->opt.rank != r || m->comm_ready) return BA_ERR_ARG;
+  }
+  if (n == 1) return BA_OK;
+  // the peer mapping rendezvous on the communicator's barrier: one thread per rank for the set-up, like every later call
+  std::vector<int> rcs(n, BA_OK);
+  std::vector<std::thread> th;
+  for (int r = 0; r < n; ++r) {
+    solvers[r]->impl->local = lc;
+    th.emplace_back([&, r] { rcs[r] = solvers[r]->impl->setup_p2p(); });
+  }
+  for (auto &t : th) t.join();
+  for (int r = 0; r < n; ++r) if (rcs[r] != BA_OK) return rcs[r];
+  return BA_OK;
 }
 
 #define BA_FWD(call) \

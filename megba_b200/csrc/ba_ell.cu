@@ -717,7 +717,7 @@ static cudaError_t launch_schur_ell_v(const Dev<T> &d, const T *xin, T *sout, T 
   auto kern = k_schur_ell<T, STORE, MODE, INFO, RC>;
   constexpr size_t smem = schur_ell_smem<T>();
   const int grid = ell_grid(d.nW);
-  if (check_active && pdl_enabled()) {
+  if (check_active && pdl_enabled() && !d.no_pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(ELL_THREADS);
@@ -792,7 +792,7 @@ static cudaError_t launch_schur_tma_v(const Dev<T> &d, const T *xin, T *sout, T 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (check_active && pdl_enabled()) ? 1 : 0;
+  cfg.numAttrs = (check_active && pdl_enabled() && !d.no_pdl) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, d, xin, sout, zero_set, check_active);
 }
 

@@ -64,8 +64,9 @@ struct PcgState {
 };
 
 // Peer-memory exchange descriptor of the fused allreduce inside the camera-space PCG kernel (world_size > 1).
-// data[r] -> rank r's exchange buffer [2 parity][2 vectors][9nC] (IPC-mapped for r != rank), flag[r] -> its two
-// 64-bit epoch flags.  ws == 1 disables the exchange.
+// data[r] -> rank r's inbox [2 parity][ws senders][2 vectors][9nC] (IPC-mapped for r != rank), flag[r] -> its
+// [2 parity][8 senders] 64-bit epoch flags.  Ranks PUSH their partial vectors and flags into the peers' memory and
+// poll / read only their own.  ws == 1 disables the exchange.
 struct PeerExchange {
   void *data[8];
   unsigned long long *flag[8];
@@ -82,6 +83,8 @@ struct Dev {
   // sizes
   int nC, nPl, nT, nSlabs, nChunks, nEl;
   int implicit;
+  int no_pdl;                   // several ranks share this device (in-process communicator): no programmatic dependent launch,
+                                // an early-launched grid parked at griddepcontrol.wait would starve the peer it waits for
   // point-major static graph
   const int4 *tile;             // {slot0, ne, pt0, np}
   const int *e_cam;
@@ -142,6 +145,7 @@ template <typename T> bool pcg_reg_kernel_available(const Dev<T> &d);
 template <typename T> cudaError_t launch_fold_replicas(const Dev<T> &d, T *s, int nvec, cudaStream_t st);
 template <typename T> cudaError_t launch_pad_cam(const Dev<T> &d, const T *src, cudaStream_t st);
 int pcg_cluster_size();
+template <typename U> cudaError_t launch_sum_ranks(U *dst, const void *const *srcs, int nr, size_t n, int op, cudaStream_t st);
 template <typename T> cudaError_t launch_trial(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_norms(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_apply_step(const Dev<T> &d, cudaStream_t st);

@@ -28,6 +28,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ba_geometry.cuh"
 #include "ba_internal.h"
 #include "ba_device_utils.cuh"
@@ -817,24 +819,34 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
         rj[j] = d.r[i];
       }
       p_s[l] = pj[j];
-      if (px.ws > 1) {  // publish this rank's partial sums for the peers (own HBM, read by them over NVLink)
-        T *mine = reinterpret_cast<T *>(px.data[px.rank]) + (size_t)px.parity * 2 * rs;
-        mine[i] = sb;
-        if (INIT) mine[rs + i] = sa;
+      if (px.ws > 1) {  // push this rank's partial sums into every rank's inbox (posted stores over NVLink)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (r < px.ws) {
+            T *slot = reinterpret_cast<T *>(px.data[r]) + ((size_t)(px.parity * px.ws + px.rank) * 2) * rs;
+            slot[i] = sb;
+            if (INIT) slot[rs + i] = sa;
+          }
+        }
       }
     }
   }
   if (!PRE_INV) cp_async_commit();
   if (px.ws > 1) {
-    // ---- fused allreduce over NVLink peer memory (replaces fold kernel + ncclAllReduce + a launch):
-    // every rank publishes its partial camera vector, raises a flag, waits for all flags, and sums the
-    // ws partials in rank order -- the same order on every rank, so the result is bit-identical everywhere.
+    // ---- fused allreduce over NVLink peer memory (replaces fold kernel + ncclAllReduce + a launch), push flavour:
+    // every rank has written its partial camera vector into all inboxes; once those stores are ordered (system fence
+    // by the storing threads, barrier, then a release store) it raises its flag IN EVERY PEER'S memory.  A rank then
+    // polls only its own, local flags and sums its local inbox in rank order -- the same order on every rank, so the
+    // result is bit-identical everywhere -- i.e. one NVLink traversal on the critical path instead of a remote flag
+    // poll followed by remote loads.  Inboxes and flags are double-buffered by epoch parity: a rank can be at most one
+    // exchange ahead of a peer (it needs the peer's flag of exchange k to finish k), so parity k is never rewritten
+    // while someone still reads it.
     __threadfence_system();
     cl.sync();
-    if (rank == 0 && tid == 0)
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flag[px.rank] + px.parity), "l"(px.epoch) : "memory");
+    if (rank == 0 && tid < px.ws)
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flag[tid] + px.parity * 8 + px.rank), "l"(px.epoch) : "memory");
     if (tid < px.ws) {
-      const unsigned long long *f = px.flag[tid] + px.parity;
+      const unsigned long long *f = px.flag[px.rank] + px.parity * 8 + tid;
       unsigned long long v = 0;
       const long long t0 = clock64();
       do {
@@ -848,15 +860,15 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
       const int l = tid + j * PCG_THREADS;
       if (l < nrows) {
         const int i = i0 + l;
-        // all peer loads are issued before the first add: a rolled loop would pay one NVLink round trip per rank
+        // all inbox loads are issued before the first add
         T pb[8], pa[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           pb[r] = pa[r] = T(0);
           if (r < px.ws) {
-            const T *peer = reinterpret_cast<const T *>(px.data[r]) + (size_t)px.parity * 2 * rs;
-            pb[r] = __ldcv(peer + i);
-            if (INIT) pa[r] = __ldcv(peer + rs + i);
+            const T *slot = reinterpret_cast<const T *>(px.data[px.rank]) + ((size_t)(px.parity * px.ws + r) * 2) * rs;
+            pb[r] = __ldcv(slot + i);
+            if (INIT) pa[r] = __ldcv(slot + rs + i);
           }
         }
         T sb = T(0), sa = T(0);
@@ -1210,7 +1222,7 @@ static void launch_schur_edge_v(const Dev<T> &d, const T *xin, T *sout, T *zero_
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     *prepared = true;
   }
-  if (check_active && pdl_enabled()) {
+  if (check_active && pdl_enabled() && !d.no_pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(d.nT);
     cfg.blockDim = dim3(TE);
@@ -1271,7 +1283,7 @@ static cudaError_t launch_cluster(K kernel, int cl, size_t smem, const Dev<T> &d
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // may be scheduled during the edge pass's tail
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = (pdl_enabled() && !d.no_pdl) ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, d, sB, max_iter, tol, refuse, nrep, extra...);
 }
 
@@ -1436,6 +1448,31 @@ cudaError_t launch_cam_matvec_sub(const Dev<T> &d, const T *p, const T *s, T *q,
   k_cam_matvec_sub<T><<<(9 * d.nC + 255) / 256, 256, 0, st>>>(d, p, s, q);
   return cudaGetLastError();
 }
+
+// dst[i] = op over r of src[r][i], in rank order (in-process communicator, ba_api.cu)
+struct RankPtrs { const void *p[8]; };
+template <typename U>
+__global__ void __launch_bounds__(256) k_sum_ranks(U *dst, RankPtrs src, int nr, size_t n, int op) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    U a = reinterpret_cast<const volatile U *>(src.p[0])[i];
+    for (int r = 1; r < nr; ++r) {
+      const U b = reinterpret_cast<const volatile U *>(src.p[r])[i];
+      a = op == 0 ? a + b : op == 1 ? (a > b ? a : b) : (a < b ? a : b);
+    }
+    dst[i] = a;
+  }
+}
+template <typename U>
+cudaError_t launch_sum_ranks(U *dst, const void *const *srcs, int nr, size_t n, int op, cudaStream_t st) {
+  RankPtrs rp{};
+  for (int r = 0; r < nr && r < 8; ++r) rp.p[r] = srcs[r];
+  const int grid = (int)std::min<size_t>((n + 255) / 256, 592);
+  if (n) k_sum_ranks<U><<<grid, 256, 0, st>>>(dst, rp, nr, n, op);
+  return cudaGetLastError();
+}
+template cudaError_t launch_sum_ranks<double>(double *, const void *const *, int, size_t, int, cudaStream_t);
+template cudaError_t launch_sum_ranks<float>(float *, const void *const *, int, size_t, int, cudaStream_t);
 
 #define BA_INSTANTIATE(T)                                                                                   \
   template cudaError_t launch_linearize<T>(const Dev<T> &, cudaStream_t);                                   \
