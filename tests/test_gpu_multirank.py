@@ -1,5 +1,6 @@
-"""Two ranks, two GPUs, NCCL: the point-sharded CUDA path reproduces the single-rank oracle.
-Skipped when fewer than two GPUs are visible (run with `gpurun --gpus 2`)."""
+"""Two ranks, two GPUs, NCCL + CUDA IPC: the point-sharded CUDA path reproduces the single-rank oracle.
+Deselected when fewer than two GPUs are visible (tests/conftest.py; run with `gpurun --gpus 2`) -- the same sharded path with
+all ranks on one device is tests/test_gpu_sharded_one_device.py."""
 import os
 import socket
 import time
@@ -55,7 +56,7 @@ def _worker(rank, ws, uid_path, out_path, implicit):
     S.close()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+@pytest.mark.two_gpus
 @pytest.mark.parametrize("implicit", [False, True])
 @pytest.mark.timeout(600)
 def test_two_gpus_match_single_rank_oracle(tmp_path, implicit):
@@ -94,7 +95,7 @@ def test_two_gpus_match_single_rank_oracle(tmp_path, implicit):
     assert np.array_equal(r0["pt"], r1["pt"])                       # get_params gathers the full point array on every rank
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+@pytest.mark.two_gpus
 @pytest.mark.timeout(600)
 def test_facade_world_size_two_threads_in_one_process(tmp_path):
     """The C++ facade drives deviceUsed = {0, 1} from two host threads of ONE process (like the reference's single
