@@ -192,6 +192,15 @@ int ba_comm_init_local(ba_solver **solvers, int32_t n);
 int ba_set_params(ba_solver *s, const void *cam, const void *pt);
 int ba_get_params(ba_solver *s, void *cam, void *pt);
 
+/* Device-pointer variants of the two calls above -- the reference's seams hand raw device pointers around
+ * (include/solver/base_solver.h:28-32, src/solver/schur_pcg_solver.cu:599-608), and a caller that already holds x
+ * on the GPU must not bounce through the host.  cam / pt are DEVICE buffers on the solver's device, same shapes and
+ * vertex order as above; nothing is synchronised with the host.  `stream` (a cudaStream_t, may be NULL) is the
+ * caller's stream: the copies are ordered after the work already enqueued on it, and work enqueued on it afterwards
+ * is ordered after them.  ba_get_params_device is for single-rank solvers.                                        */
+int ba_set_params_device(ba_solver *s, const void *cam_dev, const void *pt_dev, void *stream);
+int ba_get_params_device(ba_solver *s, void *cam_dev, void *pt_dev, void *stream);
+
 /* Optional per-edge 2x2 information matrices, info[nE][4] row-major
  * (BaseEdge::setInformation; JMulInfo/makeHSchurWithInfo,
  * src/edge/build_linear_system.cu:149-239).  NULL restores identity.  In the default
@@ -217,6 +226,13 @@ int ba_process_diag(ba_solver *s, double region, int recover);
  * src/solver/implicit_schur_pcg_solver.cu:661-720): block inverses, Schur RHS,
  * warm-started PCG, back-substitution.  Result in the solver's deltaX.            */
 int ba_solve(ba_solver *s, const ba_pcg_options *opt, int32_t *iters, int32_t *done);
+
+/* The same solve without host synchronisation: ba_solve_async enqueues all launches (max_iter PCG iterations; those
+ * past the end of the reference's loop are no-ops on the device) on the solver's stream and returns; ba_solve_wait
+ * blocks until they are done and reports the iteration count.  Exactly one ba_solve_wait per ba_solve_async, before
+ * any other call that reads the step.                                                                             */
+int ba_solve_async(ba_solver *s, const ba_pcg_options *opt);
+int ba_solve_wait(ba_solver *s, int32_t *iters, int32_t *done);
 
 /* ||deltaX||_2 and ||x||_2 (l2NormPow2, src/algo/lm_algo.cu:54-58,172-175).       */
 int ba_step_norms(ba_solver *s, double *dx_norm, double *x_norm);

@@ -24,7 +24,8 @@ BUF_HPP, BUF_HLL, BUF_W, BUF_J, BUF_G, BUF_DX = range(6)
 SYMBOLS = [
     "ba_abi_version", "ba_partition_points", "ba_create", "ba_destroy", "ba_last_error",
     "ba_comm_unique_id", "ba_comm_init", "ba_comm_init_local", "ba_set_params", "ba_get_params", "ba_set_information",
-    "ba_linearize", "ba_process_diag", "ba_solve", "ba_step_norms", "ba_eval_trial",
+    "ba_linearize", "ba_process_diag", "ba_solve", "ba_solve_async", "ba_solve_wait",
+    "ba_set_params_device", "ba_get_params_device", "ba_step_norms", "ba_eval_trial",
     "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
     "ba_eval_edges", "ba_schur_apply", "ba_set_timing", "ba_reset_stats", "ba_get_stats",
     "ba_algorithmic_bytes", "ba_stream", "ba_layout", "ba_layout_ell",
@@ -85,7 +86,8 @@ def load():
                                 C.c_void_p, C.POINTER(C.c_void_p)]
         L.ba_partition_points.argtypes = [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
         for name in ("ba_comm_init", "ba_set_params", "ba_get_params", "ba_set_information", "ba_linearize",
-                     "ba_solve", "ba_step_norms", "ba_eval_trial", "ba_accept_step", "ba_reject_step",
+                     "ba_solve", "ba_solve_async", "ba_solve_wait", "ba_set_params_device", "ba_get_params_device",
+                     "ba_step_norms", "ba_eval_trial", "ba_accept_step", "ba_reject_step",
                      "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx", "ba_eval_edges",
                      "ba_schur_apply", "ba_set_timing", "ba_reset_stats", "ba_get_stats",
                      "ba_algorithmic_bytes"):
@@ -266,6 +268,23 @@ class Solver:
         it, done = C.c_int32(), C.c_int32()
         self._chk(self.L.ba_solve(self.h, C.byref(o), C.byref(it), C.byref(done)), "ba_solve")
         return it.value, bool(done.value)
+
+    def solve_async(self, max_iter=100, tol=1e-1, refuse_ratio=1.0):
+        o = PcgOptions(max_iter, 0, tol, refuse_ratio)
+        self._chk(self.L.ba_solve_async(self.h, C.byref(o)), "ba_solve_async")
+
+    def solve_wait(self):
+        it, done = C.c_int32(), C.c_int32()
+        self._chk(self.L.ba_solve_wait(self.h, C.byref(it), C.byref(done)), "ba_solve_wait")
+        return it.value, bool(done.value)
+
+    def set_params_device(self, cam_ptr: int, pt_ptr: int, stream: int = 0):
+        self._chk(self.L.ba_set_params_device(self.h, C.c_void_p(cam_ptr), C.c_void_p(pt_ptr), C.c_void_p(stream)),
+                  "ba_set_params_device")
+
+    def get_params_device(self, cam_ptr: int, pt_ptr: int, stream: int = 0):
+        self._chk(self.L.ba_get_params_device(self.h, C.c_void_p(cam_ptr), C.c_void_p(pt_ptr), C.c_void_p(stream)),
+                  "ba_get_params_device")
 
     def step_norms(self):
         a, b = C.c_double(), C.c_double()

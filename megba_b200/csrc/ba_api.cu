@@ -383,6 +383,10 @@ struct Impl {
   virtual int linearize(double *cost) = 0;
   virtual int process_diag(double region, int recover) = 0;
   virtual int solve(const ba_pcg_options *o, int *iters, int *done) = 0;
+  virtual int solve_async(const ba_pcg_options *o) = 0;
+  virtual int solve_wait(int *iters, int *done) = 0;
+  virtual int set_params_device(const void *cam, const void *pt, void *caller_stream) = 0;
+  virtual int get_params_device(void *cam, void *pt, void *caller_stream) = 0;
   virtual int step_norms(double *dx, double *x) = 0;
   virtual int eval_trial(double *cost_new, double *model_sq) = 0;
   virtual int accept_step() = 0;
@@ -418,6 +422,9 @@ struct ImplT : Impl {
   size_t ev_used = 0;
   std::vector<size_t> ev_schur, ev_lin, ev_pcg, ev_solve, ev_cam;
   int pcg_chunk = 8;
+  int launched = 0;             // PCG iterations enqueued by the current / last solve
+  bool solve_pending = false;   // ba_solve_async enqueued, ba_solve_wait not yet called
+  std::vector<std::pair<size_t, int>> loc_schur, loc_cam;  // (event pair, iteration) of the sampled launches
   // fused peer-memory exchange of the camera kernel (world_size > 1)
   void *xchg = nullptr;
   void *ipc_opened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -752,6 +759,58 @@ struct ImplT : Impl {
     return BA_OK;
   }
 
+  // Device-pointer variants (the reference's raw-pointer seam, include/solver/base_solver.h:28-32): buffers live on THIS
+  // solver's device, in the caller's vertex order; no host copy, no host synchronisation.  `caller_stream` (may be
+  // null) is ordered with the solver's stream through events: the copies start after the work already enqueued on it,
+  // and work enqueued on it afterwards sees the results.
+  int link_in(void *caller_stream) {
+    if (!caller_stream) return BA_OK;
+    BA_CUDA(cudaEventRecord(st_event[0], (cudaStream_t)caller_stream));
+    BA_CUDA(cudaStreamWaitEvent(stream, st_event[0], 0));
+    return BA_OK;
+  }
+  int link_out(void *caller_stream) {
+    if (!caller_stream) return BA_OK;
+    BA_CUDA(cudaEventRecord(st_event[1], stream));
+    BA_CUDA(cudaStreamWaitEvent((cudaStream_t)caller_stream, st_event[1], 0));
+    return BA_OK;
+  }
+  int set_params_device(const void *cam_v, const void *pt_v, void *caller_stream) override {
+    if (!cam_v || !pt_v) return fail(BA_ERR_ARG, "null parameter buffer");
+    if (solve_pending) return fail(BA_ERR_STATE, "ba_solve_async is still pending");
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_TRY(link_in(caller_stream));
+    const T *cam = (const T *)cam_v, *pt = (const T *)pt_v;
+    BA_CUDA(cudaMemcpyAsync(d.cam, cam, sizeof(T) * 9 * g.nC, cudaMemcpyDeviceToDevice, stream));
+    if (g.nPl) {
+      if (g.ell) BA_CUDA(launch_permute3<T>(pt + 3 * g.pt_begin, d.pt, perm_dev, g.nPl, 1, stream));
+      else BA_CUDA(cudaMemcpyAsync(d.pt, pt + 3 * g.pt_begin, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
+    }
+    if (g.ell) { BA_CUDA(launch_cam_consts<T>(d, stream)); stats.launches += g.nPl ? 2 : 1; }
+    BA_CUDA(cudaMemsetAsync(d.dxc, 0, sizeof(T) * 9 * g.nC, stream));
+    BA_CUDA(cudaMemsetAsync(d.dxc_bk, 0, sizeof(T) * 9 * g.nC, stream));
+    if (g.nPl) {
+      BA_CUDA(cudaMemsetAsync(d.dxl, 0, sizeof(T) * 3 * g.nPl, stream));
+      BA_CUDA(cudaMemsetAsync(d.dxl_bk, 0, sizeof(T) * 3 * g.nPl, stream));
+    }
+    BA_TRY(link_out(caller_stream));  // the caller may reuse its buffers once its stream passes this point
+    linearized = false;
+    return BA_OK;
+  }
+  int get_params_device(void *cam_v, void *pt_v, void *caller_stream) override {
+    if (!cam_v || !pt_v) return fail(BA_ERR_ARG, "null parameter buffer");
+    if (opt.world_size > 1) return fail(BA_ERR_STATE, "ba_get_params_device: single-rank solvers only (use ba_get_params)");
+    BA_CUDA(cudaSetDevice(opt.device));
+    BA_TRY(link_in(caller_stream));
+    T *cam = (T *)cam_v, *pt = (T *)pt_v;
+    BA_CUDA(cudaMemcpyAsync(cam, d.cam, sizeof(T) * 9 * g.nC, cudaMemcpyDeviceToDevice, stream));
+    if (g.nPl) {
+      if (g.ell) { BA_CUDA(launch_permute3<T>(d.pt, pt, perm_dev, g.nPl, 0, stream)); stats.launches += 1; }
+      else BA_CUDA(cudaMemcpyAsync(pt, d.pt, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
+    }
+    return link_out(caller_stream);
+  }
+
   int set_information(const void *info_v) override {
     BA_CUDA(cudaSetDevice(opt.device));
     if (!info_v) {
@@ -879,9 +938,23 @@ struct ImplT : Impl {
     return BA_OK;
   }
 
+  // ba_solve = enqueue + finish.  ba_solve_async enqueues every launch of the solve (no polling: iterations past the
+  // end of the reference's do-while are no-ops on the device) and returns without a host synchronisation;
+  // ba_solve_wait fetches the final PCG state.
   int solve(const ba_pcg_options *o, int *iters, int *done) override {
+    BA_TRY(solve_enqueue(o, true));
+    return solve_finish(iters, done);
+  }
+  int solve_async(const ba_pcg_options *o) override { return solve_enqueue(o, false); }
+  int solve_wait(int *iters, int *done) override {
+    if (!solve_pending) return fail(BA_ERR_STATE, "ba_solve_wait without ba_solve_async");
+    return solve_finish(iters, done);
+  }
+
+  int solve_enqueue(const ba_pcg_options *o, bool polling) {
     if (!o) return fail(BA_ERR_ARG, "null pcg options");
     if (!linearized) return fail(BA_ERR_STATE, "ba_solve before ba_linearize");
+    if (solve_pending) return fail(BA_ERR_STATE, "ba_solve_async is still pending: call ba_solve_wait first");
     BA_CUDA(cudaSetDevice(opt.device));
     size_t ev_s = 0, ev_p = 0;
     if (timing) ev_s = ev_begin();
@@ -922,9 +995,11 @@ struct ImplT : Impl {
     // The loop is enqueued in chunks; the device-side `active` flag turns the remaining launches of a
     // chunk into no-ops once the reference's do-while would have exited.  The state of chunk k is polled
     // only after chunk k+1 has been enqueued, so the GPU never waits for the host.
-    int launched = 0, chunk_id = 0;
+    int chunk_id = 0;
+    launched = 0;
     struct Pending { int slot; bool valid; } pend{0, false};
-    std::vector<std::pair<size_t, int>> loc_schur, loc_cam;  // (event pair, iteration) of the sampled launches
+    loc_schur.clear();
+    loc_cam.clear();
     bool finished = false;
     auto poll = [&](const Pending &pd) -> int {
       BA_CUDA(cudaEventSynchronize(st_event[pd.slot]));
@@ -960,7 +1035,7 @@ struct ImplT : Impl {
       const int slot = chunk_id++ & 1;
       BA_CUDA(cudaMemcpyAsync(&h_st[slot], d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
       BA_CUDA(cudaEventRecord(st_event[slot], stream));
-      if (pend.valid) BA_TRY(poll(pend));
+      if (pend.valid && polling) BA_TRY(poll(pend));
       pend = Pending{slot, true};
     }
     if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); }
@@ -975,6 +1050,13 @@ struct ImplT : Impl {
       stats.launches += 2;
       BA_TRY(allreduce_scal(S_DX2_PT, 2, ncclSum));
     }
+    solve_pending = true;
+    return BA_OK;
+  }
+
+  int solve_finish(int *iters, int *done) {
+    BA_CUDA(cudaSetDevice(opt.device));
+    solve_pending = false;
     {
       // final state (also covers the over-enqueued chunk)
       BA_CUDA(cudaMemcpyAsync(&h_st[0], d.st, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
@@ -1428,6 +1510,10 @@ int ba_set_information(ba_solver *s, const void *info) { BA_FWD(set_information(
 int ba_linearize(ba_solver *s, double *cost) { BA_FWD(linearize(cost)); }
 int ba_process_diag(ba_solver *s, double region, int recover) { BA_FWD(process_diag(region, recover)); }
 int ba_solve(ba_solver *s, const ba_pcg_options *o, int32_t *iters, int32_t *done) { BA_FWD(solve(o, iters, done)); }
+int ba_solve_async(ba_solver *s, const ba_pcg_options *o) { BA_FWD(solve_async(o)); }
+int ba_solve_wait(ba_solver *s, int32_t *iters, int32_t *done) { BA_FWD(solve_wait(iters, done)); }
+int ba_set_params_device(ba_solver *s, const void *cam, const void *pt, void *stream) { BA_FWD(set_params_device(cam, pt, stream)); }
+int ba_get_params_device(ba_solver *s, void *cam, void *pt, void *stream) { BA_FWD(get_params_device(cam, pt, stream)); }
 int ba_step_norms(ba_solver *s, double *a, double *b) { BA_FWD(step_norms(a, b)); }
 int ba_eval_trial(ba_solver *s, double *a, double *b) { BA_FWD(eval_trial(a, b)); }
 int ba_accept_step(ba_solver *s) { BA_FWD(accept_step()); }

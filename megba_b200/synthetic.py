@@ -71,8 +71,45 @@ def project(cam: np.ndarray, X: np.ndarray) -> np.ndarray:
     return (cam[:, 6] * rp)[:, None] * B
 
 
+def _bal_like_graph(nC: int, nP: int, nE: int, rng) -> tuple[np.ndarray, np.ndarray]:
+    """Observation graph with the statistics of real BAL problems instead of a uniform random one: heavy-tailed track
+    lengths (most points seen 2-4 times, a few by hundreds of cameras) and spatially coherent camera sets (cameras are
+    ordered along a trajectory; a point is seen by cameras of one window of it, so neighbouring cameras share points
+    and camera degrees are skewed).  Returns (pt_idx, cam_idx), point-major, camera-ascending inside a point."""
+    raw = rng.pareto(1.6, nP) + 0.05
+    deg = 2 + rng.multinomial(nE - 2 * nP, raw / raw.sum())
+    cap = max(2, nC // 2)
+    over = deg > cap
+    while over.any():
+        excess = int((deg[over] - cap).sum())
+        deg[over] = cap
+        room = np.flatnonzero(deg < cap)
+        w = raw[room] / raw[room].sum()
+        deg[room] += rng.multinomial(excess, w)
+        over = deg > cap
+    pt_idx = np.repeat(np.arange(nP, dtype=np.int64), deg)
+    start = np.concatenate([[0], np.cumsum(deg)[:-1]])
+    # cameras of a point: c0 + cumulative gaps (>= 1) modulo nC; mean gap <= 3 and span < nC keep them distinct and close
+    mean_gap = np.minimum(3.0, (nC - 1) / np.maximum(deg, 1) * 0.9)
+    gaps = 1 + np.floor(rng.exponential(np.repeat(np.maximum(mean_gap - 1.0, 0.0), deg))).astype(np.int64)
+    gaps[start] = 0
+    off = np.cumsum(gaps)
+    off -= np.repeat(off[start], deg)
+    span = off[start + deg - 1]
+    bad = np.repeat(span >= nC, deg)  # fall back to consecutive cameras for the few windows that came out too wide
+    if bad.any():
+        pos = np.arange(len(off)) - np.repeat(start, deg)
+        off[bad] = pos[bad]
+    hot = rng.random(nP) < 0.3  # a third of the points sit in a few dense regions of the trajectory (skewed camera degrees)
+    c0 = np.where(hot, (rng.integers(0, 4, nP) * (nC // 4) + rng.integers(0, max(nC // 16, 1), nP)) % nC, rng.integers(0, nC, nP))
+    cam_idx = (np.repeat(c0, deg) + off) % nC
+    key = pt_idx * nC + cam_idx
+    order = np.argsort(key, kind="stable")
+    return pt_idx[order].astype(np.int32), cam_idx[order].astype(np.int32)
+
+
 def make_synthetic(nC: int, nP: int, nE: int, seed: int = 42, noise_px: float = 0.5,
-                   label: str | None = None) -> BAProblem:
+                   label: str | None = None, graph: str = "uniform") -> BAProblem:
     from scipy.spatial.transform import Rotation
 
     if nE < 2 * nP:
@@ -101,6 +138,10 @@ def make_synthetic(nC: int, nP: int, nE: int, seed: int = 42, noise_px: float = 
     k2 = rng.normal(0.0, 6e-3, size=nC)
     cam_true = np.concatenate([omega, t, f[:, None], k1[:, None], k2[:, None]], axis=1)
     # --- graph
+    if graph == "bal":
+        pt_idx, cam_idx = _bal_like_graph(nC, nP, nE, rng)
+        return _finish(nC, nP, nE, cam_idx, pt_idx, cam_true, X, rng, noise_px,
+                       label or f"synthetic-bal-{nC}-{nP}-{nE}-seed{seed}")
     deg = np.full(nP, 2, dtype=np.int64)
     extra = nE - 2 * nP
     if extra:
@@ -132,6 +173,11 @@ def make_synthetic(nC: int, nP: int, nE: int, seed: int = 42, noise_px: float = 
     order = np.argsort(key, kind="stable")
     pt_idx = pt_idx[order].astype(np.int32)
     cam_idx = cam_idx[order].astype(np.int32)
+    return _finish(nC, nP, nE, cam_idx, pt_idx, cam_true, X, rng, noise_px,
+                   label or f"synthetic-{nC}-{nP}-{nE}-seed{seed}")
+
+
+def _finish(nC, nP, nE, cam_idx, pt_idx, cam_true, X, rng, noise_px, label) -> BAProblem:
     # --- observations and the perturbed initial estimate
     obs = project(cam_true[cam_idx], X[pt_idx]) + rng.normal(0.0, noise_px, size=(nE, 2))
     cam0 = cam_true.copy()
@@ -139,13 +185,17 @@ def make_synthetic(nC: int, nP: int, nE: int, seed: int = 42, noise_px: float = 
     cam0[:, 3:6] += rng.normal(0.0, 5e-2, size=(nC, 3))
     cam0[:, 6] *= 1.0 + rng.normal(0.0, 1e-2, size=nC)
     pt0 = X + rng.normal(0.0, 0.05, size=(nP, 3))
-    return BAProblem(nC, nP, nE, cam_idx, pt_idx, np.ascontiguousarray(obs), cam0, pt0,
-                     label or f"synthetic-{nC}-{nP}-{nE}-seed{seed}")
+    return BAProblem(nC, nP, nE, cam_idx, pt_idx, np.ascontiguousarray(obs), cam0, pt0, label)
 
 
 def make_named(name: str, seed: int = 42) -> BAProblem:
-    nC, nP, nE = BAL_SHAPES[name]
-    return make_synthetic(nC, nP, nE, seed=seed, label=f"synthetic:{name}")
+    """`venice-1778` = uniform random graph of that shape (the headline workload since round 1); `venice-1778:bal` = the
+    same shape with BAL-like statistics (heavy-tailed tracks, coherent camera windows)."""
+    base, _, kind = name.partition(":")
+    nC, nP, nE = BAL_SHAPES[base]
+    if kind == "bal":
+        return make_synthetic(nC, nP, nE, seed=seed, label=f"synthetic-bal:{base}", graph="bal")
+    return make_synthetic(nC, nP, nE, seed=seed, label=f"synthetic:{base}")
 
 
 def write_bal(path: str, prob: BAProblem) -> None:

@@ -9,7 +9,7 @@ import pytest
 
 from megba_b200 import capi
 from oracle.oracle import Oracle
-from util import TOL, bigpoint_problem, medium_problem, rel_fro, small_problem
+from util import TOL, bal_like_problem, bigpoint_problem, medium_problem, rel_fro, small_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,7 @@ FLAVOURS = {
     "tile-w": (capi.LAYOUT_TILE, capi.STORE_AUTO, False),
     "tile-j": (capi.LAYOUT_TILE, capi.STORE_AUTO, True),
 }
-PROBLEMS = {"small": small_problem, "medium": medium_problem, "bigpoint": bigpoint_problem}
+PROBLEMS = {"small": small_problem, "medium": medium_problem, "bigpoint": bigpoint_problem, "bal": bal_like_problem}
 
 
 def _solver(P, dtype, flavour):
@@ -43,7 +43,7 @@ def _oracle_step(P, dtype, region, n_it, info=None, dx0=None):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("name", ["small", "medium", "bigpoint"])
+@pytest.mark.parametrize("name", ["small", "medium", "bigpoint", "bal"])
 @pytest.mark.parametrize("flavour", list(FLAVOURS))
 def test_flavour_linearize_operator_pcg(flavour, name, dtype):
     P = PROBLEMS[name]()
@@ -133,3 +133,19 @@ def test_layout_store_combinations_are_validated():
         capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, layout=capi.LAYOUT_ELL, store=capi.STORE_W)
     with pytest.raises(RuntimeError):
         capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, layout=capi.LAYOUT_TILE, store=capi.STORE_FACT)
+
+
+@pytest.mark.parametrize("flavour", ["ell-fact", "tile-w"])
+def test_lm_trace_on_bal_like_graph(flavour):
+    """Whole LM runs (accept / reject sequence, costs, final parameters) on the heavy-tailed, camera-coherent graph."""
+    P = bal_like_problem()
+    S = _solver(P, np.float64, flavour)
+    O = Oracle(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, np.float64)
+    kw = dict(lm_max_iter=6, initial_region=1e3, eps1=1e-3, eps2=1e-12, pcg_max_iter=30, pcg_tol=1e-3, pcg_refuse=1.0)
+    tr = S.lm_solve(**kw)
+    x1, _, tr0 = O.lm_solve(P.x(), **kw)
+    assert [r["accepted"] for r in tr] == [r["accepted"] for r in tr0]
+    assert [r["pcg_iters"] for r in tr] == [r["pcg_iters"] for r in tr0]
+    assert np.allclose([r["cost"] for r in tr], [r["cost"] for r in tr0], rtol=1e-8)
+    cam, pt = S.get_params()
+    assert rel_fro(np.concatenate([cam.ravel(), pt.ravel()]), x1) <= 1e-7

@@ -405,3 +405,50 @@ def test_empty_graph_and_unobserved_vertices():
     it, done = S.solve(max_iter=10, tol=0.0, refuse_ratio=1e300)
     dx = S.read(capi.BUF_DX)
     assert np.all(np.isfinite(dx)) and np.all(dx[9 * 5:9 * 6] == 0) and np.all(dx[9 * 6 + 21:] == 0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_device_pointer_and_async_entry_points(dtype):
+    """ba_set_params_device / ba_get_params_device (caller-owned device buffers, ordered through the caller's stream) and
+    ba_solve_async / ba_solve_wait give the results of their host-buffer / blocking counterparts."""
+    import torch
+    P = medium_problem()
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    cam_d = torch.tensor(P.cam, dtype=tdt, device="cuda")
+    pt_d = torch.tensor(P.pt, dtype=tdt, device="cuda")
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    A = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype=dtype)
+    B = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype=dtype)
+    A.set_params(P.cam, P.pt)
+    with torch.cuda.stream(st):
+        cam_s, pt_s = cam_d * 1.0, pt_d * 1.0  # produced ON the caller's stream: the solver must wait for them
+        B.set_params_device(cam_s.data_ptr(), pt_s.data_ptr(), st.cuda_stream)
+    ca, cb = A.linearize(), B.linearize()
+    assert ca == cb
+    A.process_diag(1e3)
+    B.process_diag(1e3)
+    ita, _ = A.solve(max_iter=12, tol=0.0, refuse_ratio=1e300)
+    B.solve_async(max_iter=12, tol=0.0, refuse_ratio=1e300)
+    with pytest.raises(RuntimeError):
+        B.solve_async(max_iter=12, tol=0.0, refuse_ratio=1e300)  # one pending solve at a time
+    itb, _ = B.solve_wait()
+    assert ita == itb == 12
+    t = TOL[np.dtype(dtype)]["dx"]
+    assert rel_fro(B.read(capi.BUF_DX), A.read(capi.BUF_DX)) <= t  # same kernels; only the RED order differs
+    # early exit by the reference's rules without host polling
+    B.solve_async(max_iter=100, tol=1e-1, refuse_ratio=1.0)
+    itc, donec = B.solve_wait()
+    itd, doned = A.solve(max_iter=100, tol=1e-1, refuse_ratio=1.0)  # same warm start (the 12-iteration step) as B had
+    assert (itc, donec) == (itd, doned)
+    A.accept_step()
+    B.accept_step()
+    cam_o, pt_o = torch.empty_like(cam_d), torch.empty_like(pt_d)
+    with torch.cuda.stream(st):
+        B.get_params_device(cam_o.data_ptr(), pt_o.data_ptr(), st.cuda_stream)
+        cam_o2 = cam_o + 0.0  # consumed on the caller's stream without a host synchronisation
+    st.synchronize()
+    cam_b, pt_b = B.get_params()
+    assert np.array_equal(cam_o2.cpu().numpy(), cam_b) and np.array_equal(pt_o.cpu().numpy(), pt_b)
+    cam_a, pt_a = A.get_params()
+    assert rel_fro(cam_b, cam_a) <= t and rel_fro(pt_b, pt_a) <= t

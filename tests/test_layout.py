@@ -5,7 +5,7 @@ import pytest
 
 from megba_b200 import capi
 from megba_b200.synthetic import make_synthetic
-from util import bigpoint_problem, small_problem
+from util import bal_like_problem, bigpoint_problem, small_problem
 
 TE, CM_CHUNK = 256, 1024
 
@@ -20,10 +20,11 @@ def _problems():
         "ragged": (ragged.nC, ragged.nP, ragged.cam_idx[keep], ragged.pt_idx[keep]),
         "single_obs_points": (5, 1000, rng.integers(0, 5, 1000).astype(np.int32), np.arange(1000, dtype=np.int32)),
         "empty": (3, 4, np.zeros(0, np.int32), np.zeros(0, np.int32)),
+        "bal": (bal_like_problem().nC, bal_like_problem().nP, bal_like_problem().cam_idx, bal_like_problem().pt_idx),
     }
 
 
-@pytest.mark.parametrize("name", ["small", "bigpoint", "ragged", "single_obs_points", "empty"])
+@pytest.mark.parametrize("name", ["small", "bigpoint", "ragged", "single_obs_points", "empty", "bal"])
 @pytest.mark.parametrize("ws", [1, 2, 3])
 def test_layout_invariants(name, ws):
     nC, nP, cam_idx, pt_idx = _problems()[name]
@@ -90,7 +91,7 @@ def test_layout_rejects_bad_input():
         capi.layout(1 << 24, 2, np.array([0], np.int32), np.array([0], np.int32))  # camera count beyond the packed index
 
 
-@pytest.mark.parametrize("name", ["small", "bigpoint", "ragged", "single_obs_points", "empty"])
+@pytest.mark.parametrize("name", ["small", "bigpoint", "ragged", "single_obs_points", "empty", "bal"])
 @pytest.mark.parametrize("ws", [1, 2, 3])
 def test_ell_layout_invariants(name, ws):
     """The default (ELL) layout: device order sorted by observation count, heavy points in warps of their own,

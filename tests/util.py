@@ -57,3 +57,10 @@ def bigpoint_problem(seed=3) -> BAProblem:
     from megba_b200.synthetic import project
     obs = project(P.cam[cam_idx], P.pt[pt_idx]) + rng.normal(0, 0.5, size=(len(cam_idx), 2))
     return BAProblem(600, 900, len(cam_idx), cam_idx, pt_idx, np.ascontiguousarray(obs), P.cam, P.pt, "bigpoint")
+
+
+@functools.lru_cache(maxsize=None)
+def bal_like_problem(seed=5) -> BAProblem:
+    """BAL-like statistics (megba_b200.synthetic._bal_like_graph): heavy-tailed track lengths up to nC/2 (points with a
+    warp of their own in the ELL layout, multi-slab points in the tile layout) and coherent camera windows."""
+    return make_synthetic(120, 4000, 24000, seed=seed, graph="bal")
