@@ -291,6 +291,12 @@ int ba_get_stats(ba_solver *s, ba_stats *out);
 /* Algorithmic bytes of one S*p edge-kernel launch and one linearisation on THIS
  * rank (SURVEY.md section 8d formulas).                             */
 int ba_algorithmic_bytes(ba_solver *s, double *schur_apply_bytes, double *linearize_bytes);
+/* on != 0: ba_solve runs the whole PCG solve (MakeV + S*x0, the do-while, back-substitution) as ONE persistent
+ * cooperative kernel -- edge phases and camera phases separated by grid barriers -- where it is available (default
+ * layout and stream, ranks on distinct devices).  Off by default: on one B200 it measured 210 us per PCG iteration
+ * against 194 us for two launches per iteration chained by programmatic dependent launch (profiles/README.md).
+ * Results are identical up to the summation order of the scatter.  Environment override: BA_PERSIST=0/1.           */
+int ba_set_persistent(ba_solver *s, int32_t on);
 /* The CUDA stream (cudaStream_t) all of this solver's work is enqueued on.         */
 void *ba_stream(ba_solver *s);
 

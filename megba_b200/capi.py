@@ -28,7 +28,7 @@ SYMBOLS = [
     "ba_set_params_device", "ba_get_params_device", "ba_step_norms", "ba_eval_trial",
     "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
     "ba_eval_edges", "ba_schur_apply", "ba_set_timing", "ba_reset_stats", "ba_get_stats",
-    "ba_algorithmic_bytes", "ba_stream", "ba_layout", "ba_layout_ell",
+    "ba_algorithmic_bytes", "ba_stream", "ba_set_persistent", "ba_layout", "ba_layout_ell",
 ]
 
 
@@ -347,6 +347,9 @@ class Solver:
     def set_timing(self, on):
         """0/False off, 1/True every launch, N > 1 every N-th PCG iteration."""
         self._chk(self.L.ba_set_timing(self.h, int(on)), "ba_set_timing")
+
+    def set_persistent(self, on: bool):
+        self._chk(self.L.ba_set_persistent(self.h, int(bool(on))), "ba_set_persistent")
 
     def reset_stats(self):
         self._chk(self.L.ba_reset_stats(self.h), "ba_reset_stats")

@@ -366,6 +366,9 @@ struct Impl {
   // ba_lm_solve fuses the scalar kernels behind the big ones so that an LM iteration costs three host round trips
   // (solve + step norms, trial evaluation, linearisation + gradient norm) instead of five
   bool fuse_norms = false, fuse_ginf = false, norms_valid = false, ginf_valid = false;
+  bool persistent = false;      // whole PCG solve in one cooperative launch (ba_set_persistent / BA_PERSIST=1); measured slower
+                                // than two launches per iteration on one GPU (profiles/README.md), hence off by default
+  bool persistent_used = false; // the current / last solve took that path
   virtual ~Impl() {}
   int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -624,6 +627,7 @@ struct ImplT : Impl {
     add(&d.r, 9 * nC); add(&d.p, 9 * nC); add(&d.q, 9 * nC); add(&d.z, 9 * nC); add(&d.xbk, 9 * nC);
     add(&d.xpad, (size_t)CamPad<T>::N * nC);
     add(&d.st, 1); add(&d.scal, S_COUNT); add(&d.partials, nPart);
+    add(&d.pk_counters, 4); add(&d.pk_partials, 2 * 512); add(&d.pk_timers, 4);
     size_t total = 0;
     for (auto &it : items) total += (it.bytes + 255) / 256 * 256 + 256;
     BA_CUDA(cudaMalloc(&arena, total));
@@ -981,6 +985,28 @@ struct ImplT : Impl {
     //   sB = Hpl (Hll^-1 Hlp x0 - w)  so that  r0 = v - S x0 = g_c - Hpp x0 + sB   (schur_pcg_solver.cu:430-510,202-258);
     // sA (the reference's separate Hpl w) stays zero.
     BA_TRY(pad_cam(d.dxc));
+    static const int persist_env = getenv("BA_PERSIST") ? atoi(getenv("BA_PERSIST")) : -1;  // -1: follow ba_set_persistent
+    persistent_used = (persist_env < 0 ? persistent : persist_env != 0) && (!multi || fused) && pcg_persistent_available<T>(d);
+    if (persistent_used) {
+      // ---- the whole solve (MakeV + S*x0, the do-while, back-substitution) in one cooperative launch
+      BA_CUDA(cudaMemsetAsync(d.pk_counters, 0, 4 * sizeof(int), stream));
+      BA_CUDA(cudaMemsetAsync(d.pk_timers, 0, 4 * sizeof(double), stream));
+      if (fused) { pxl.epoch = px_epoch + 1; px_epoch += (unsigned long long)max_iter + 2; }
+      if (timing) ev_p = ev_begin();
+      BA_CUDA(launch_pcg_persistent<T>(d, max_iter, o->tol, o->refuse_ratio, pxl, stream));
+      if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); ev_end(ev_s); ev_solve.push_back(ev_s); }
+      stats.launches += 1;
+      launched = 0;
+      loc_schur.clear();
+      loc_cam.clear();
+      if (fuse_norms) {
+        BA_CUDA(launch_norms<T>(d, stream));
+        stats.launches += 2;
+        BA_TRY(allreduce_scal(S_DX2_PT, 2, ncclSum));
+      }
+      solve_pending = true;
+      return BA_OK;
+    }
     BA_TRY(schur_edge(SM_INIT, d.xpad, d.sB, 0, true));
     if (multi && !fused) {
       BA_CUDA(launch_fold_replicas<T>(d, d.sA, 2, stream));
@@ -1065,8 +1091,20 @@ struct ImplT : Impl {
       if (h_scal[S_XCHG_ERR] != 0.) return fail(BA_ERR_NCCL, "peer-memory exchange timed out (a rank did not arrive)");
       norms_valid = fuse_norms;
     }
+    if (persistent_used) {
+      // per-phase device time from %globaltimer (CTA 0): the edge phases are the launches of the S*p pass
+      double tm[4];
+      BA_CUDA(cudaMemcpy(tm, d.pk_timers, sizeof tm, cudaMemcpyDeviceToHost));
+      stats.schur_apply_calls += h_st[0].n + 1;
+      if (timing) {
+        stats.schur_apply_ms += tm[0] * 1e-6;
+        stats.schur_apply_timed += tm[1];
+        stats.pcg_cam_ms += tm[2] * 1e-6;
+        stats.pcg_cam_timed += tm[3];
+      }
+    }
     // inactive edge launches return immediately; only executed iterations are counted
-    stats.schur_apply_calls -= (launched - h_st[0].n);
+    if (!persistent_used) stats.schur_apply_calls -= (launched - h_st[0].n);
     // launches issued after the loop ended returned immediately: keep only the samples of iterations that ran
     for (auto &e : loc_schur) if (e.second < h_st[0].n) ev_schur.push_back(e.first);
     for (auto &e : loc_cam) if (e.second < h_st[0].n) ev_cam.push_back(e.first);
@@ -1531,6 +1569,12 @@ int ba_set_timing(ba_solver *s, int32_t on) {
   if (!s) return BA_ERR_ARG;
   s->impl->timing = on != 0;
   s->impl->timing_stride = on > 1 ? on : 1;
+  return BA_OK;
+}
+
+int ba_set_persistent(ba_solver *s, int32_t on) {
+  if (!s) return BA_ERR_ARG;
+  s->impl->persistent = on != 0;
   return BA_OK;
 }
 

@@ -40,6 +40,11 @@ template <> struct Vec2<float> { using type = float2; };
 // that consecutive lanes add consecutive components of one camera (3 RED sectors per observation
 // instead of 9), and the target vector exists in NREP replicas selected by CTA so the RED traffic is
 // spread over all L2 slices (profiles/r01_microbench_red.txt: 0.47 ms -> 0.087 ms for Venice).
+// fire-and-forget reduction: spelled in PTX because the compiler turns an unused-result atomicAdd into the returning
+// ATOMG form in some contexts (seen inside the persistent cooperative kernel), which halves the scatter rate
+__device__ __forceinline__ void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_add(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
 template <typename T>
 __device__ __forceinline__ void warp_scatter9(T *sv, int *sc, const T *o, int c, T *dst) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -53,7 +58,7 @@ __device__ __forceinline__ void warp_scatter9(T *sv, int *sc, const T *o, int c,
   for (int j = 0; j < 9; ++j) {
     const int v = j * 32 + lane, el = v / 9, k = v - 9 * el;
     const int cc = cams[el];
-    if (cc >= 0) atomicAdd(dst + 9 * (size_t)cc + k, mine[v]);
+    if (cc >= 0) red_add(dst + 9 * (size_t)cc + k, mine[v]);
   }
   __syncwarp();
 }

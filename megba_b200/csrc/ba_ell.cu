@@ -15,12 +15,15 @@
 //                   src/algo/lm_algo.cu:61-126).
 //   k_prep_points_ell <- processDiag + the 3x3 cublasXmatinvBatched + w = Hll^-1 g_l
 //                   (schur_LM_linear_system.cu:114-185, schur_pcg_solver.cu:61-97,467-476).
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 
 #include "ba_device_utils.cuh"
 #include "ba_geometry.cuh"
 #include "ba_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace ba {
 
@@ -567,6 +570,426 @@ k_schur_tma(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
 }
 
 // --------------------------------------------------------------------------------
+// Persistent PCG kernel: the whole Schur-PCG solve (SchurPCGSolver::solve, src/solver/schur_pcg_solver.cu:599-679:
+// MakeV fused with S*x0, the do-while :265-407, SolveW) in ONE cooperative launch, one CTA of 24 warps per SM.
+//   edge phase   : warps take slices from a global counter (slices are sorted by row count, so this is longest-first
+//                  scheduling); per slice exactly the two-phase pass of k_schur_ell<FACT>
+//   camera phase : the 9 nC rows are spread over all CTAs (a CTA owns whole cameras); q = Hpp p - T^T Y, alpha, x / r
+//                  update, z = Hpp^-1 r, rho, refuse / tol tests, p update, T p -> xpad; the two dot products go through
+//                  per-CTA partials summed in CTA order by every CTA (deterministic, identical everywhere)
+// separated by grid barriers (4 per iteration).  Compared with two launches per iteration this removes the launch /
+// drain gaps and runs the camera step on every SM instead of one 16-CTA cluster.  With world_size > 1 the push exchange
+// of k_pcg_cam_reg runs inside the camera phase (one more grid barrier orders the pushes before the flags go up).
+constexpr int PK_THREADS = 768;
+constexpr int PK_WARPS = PK_THREADS / 32;
+
+struct PkArgs {
+  int max_iter;
+  double tol, refuse;
+  int *counters;        // [4] slice counters of the edge phases (zero on entry)
+  double *partials;     // [2][gridDim] per-CTA partial dot products
+  double *timers;       // [4] device-timer sums: edge-phase ns, edge phases, camera-phase ns, camera phases
+};
+
+template <typename T>
+__host__ __device__ constexpr size_t pk_smem(int rpt) {
+  // scatter staging per warp + p / r / y exchange rows of the camera phase
+  return (size_t)PK_WARPS * 32 * 9 * sizeof(T) + (size_t)PK_WARPS * 32 * sizeof(int) + 3 * (size_t)rpt * PK_THREADS * sizeof(T) + 64 * sizeof(double);
+}
+
+__device__ __forceinline__ unsigned long long pk_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// The gathered vector (xpad) is rewritten by the camera phase of the SAME kernel: it must be read through the coherent
+// path (ld.global.ca is invalidated by the acquire side of the grid barrier; the non-coherent LDG.CONSTANT path of
+// __ldg carries no such guarantee inside one kernel).
+template <typename T>
+__device__ __forceinline__ void gather_cam_coherent(const T *xpad, int c, T *x) {
+  // plain (ld.global, default .ca) vector loads: no __ldg, no __restrict__, so the compiler cannot pick LDG.CONSTANT
+  using V = typename CamPad<T>::vec;
+  constexpr int NV = CamPad<T>::N * sizeof(T) / 16;
+  const V *src = reinterpret_cast<const V *>(xpad + (size_t)CamPad<T>::N * c);
+  V *xv = reinterpret_cast<V *>(x);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) xv[k] = src[k];
+}
+
+// one slice (or heavy point), both phases; MODE as in k_schur_ell
+template <typename T, int MODE, bool INFO>
+__device__ __noinline__ void pk_slice(const Dev<T> &d, const WDesc &wd, int lane, const T *xin, T *dst, T *sv, int *sc) {
+  const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
+  const bool pvalid = wd.heavy || lane < wd.np;
+  const size_t npl = (size_t)d.nPlPad;
+  T X0 = T(0), X1 = T(0), X2 = T(0);
+  if (pvalid) { X0 = __ldg(d.XP + p); X1 = __ldg(d.XP + npl + p); X2 = __ldg(d.XP + 2 * npl + p); }
+  T t0 = T(0), t1 = T(0), t2 = T(0);
+#pragma unroll 2
+  for (int r = 0; r < wd.D; ++r) {
+    const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    T s[8];
+    load_stream<T, 8>(d.WJ, row, lane, s);
+    if (c >= 0) {
+      __align__(16) T g[CamPad<T>::N];
+      gather_cam_coherent(xin, c, g);
+      T om[4];
+      if (INFO) load_info<T>(d.r_info, slot, om);
+      fact_first<T, INFO>(s, g, X0, X1, X2, om, t0, t1, t2);
+    }
+  }
+  T hi[9], wv[3] = {T(0), T(0), T(0)};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) hi[k] = T(0);
+  if (pvalid) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hi[k] = __ldg(d.HllInvP + k * npl + p);
+    if (MODE != SM_FULL) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wv[k] = __ldg(d.wP + k * npl + p);
+    }
+  }
+  if (wd.heavy) { t0 = warp_sum<T>(t0); t1 = warp_sum<T>(t1); t2 = warp_sum<T>(t2); }
+  T u0 = hi[0] * t0 + hi[1] * t1 + hi[2] * t2;
+  T u1 = hi[3] * t0 + hi[4] * t1 + hi[5] * t2;
+  T u2 = hi[6] * t0 + hi[7] * t1 + hi[8] * t2;
+  if (MODE == SM_INIT) { u0 -= wv[0]; u1 -= wv[1]; u2 -= wv[2]; }
+  if (MODE == SM_BACKSUB) {
+    if (pvalid && (!wd.heavy || lane == 0)) {
+      d.dxl[3 * (size_t)p] = wv[0] - u0;
+      d.dxl[3 * (size_t)p + 1] = wv[1] - u1;
+      d.dxl[3 * (size_t)p + 2] = wv[2] - u2;
+    }
+    return;
+  }
+  for (int r = 0; r < wd.D; ++r) {
+    const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    T s[8], o[9];
+    load_stream<T, 8>(d.WJ, row, lane, s);
+    if (c >= 0) {
+      T om[4];
+      if (INFO) load_info<T>(d.r_info, slot, om);
+      fact_second<T, INFO>(s, u0, u1, u2, X0, X1, X2, om, o);
+    }
+    warp_scatter9<T>(sv, sc, o, c, dst);
+  }
+}
+
+template <typename T, int MODE, bool INFO>
+__device__ __forceinline__ void pk_edge_phase(const Dev<T> &d, int *counter, const T *xin, T *sout, T *zero_set, T *sv, int *sc) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (zero_set) {  // clear the replica set the NEXT edge phase accumulates into
+    const unsigned tot = (unsigned)NREP * 9u * (unsigned)d.nC;
+    for (unsigned i = blockIdx.x * PK_THREADS + tid; i < tot; i += gridDim.x * PK_THREADS) zero_set[i] = T(0);
+  }
+  T *dst = MODE != SM_BACKSUB ? sout + (size_t)(blockIdx.x % NREP) * (9 * (size_t)d.nC) : nullptr;
+  auto grab = [&]() -> int {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(counter, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
+  int sidx = grab();
+  while (sidx < d.nW) {
+    const int nxt = grab();  // requested before the slice is processed: its latency hides behind the slice
+    const WDesc wd = load_desc(d.wdesc, sidx);
+    pk_slice<T, MODE, INFO>(d, wd, lane, xin, dst, sv, sc);
+    sidx = nxt;
+  }
+}
+
+// sum of the per-CTA partials, the same fixed tree on every CTA; result valid in every thread
+__device__ __forceinline__ double pk_total(const double *partials, int n, double *bcast) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    double mine = 0.;
+    for (int r = lane; r < n; r += 32) mine += __ldcg(partials + r);
+    mine = warp_sum<double>(mine);
+    if (lane == 0) *bcast = mine;
+  }
+  __syncthreads();
+  const double v = *bcast;
+  __syncthreads();
+  return v;
+}
+__device__ __forceinline__ void pk_cta_partial(double v, double *red_warp, double *out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum<double>(v);
+  if (lane == 0) red_warp[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double x = lane < PK_WARPS ? red_warp[lane] : 0.;
+    x = warp_sum<double>(x);
+    if (lane == 0) *out = x;
+  }
+  __syncthreads();
+}
+
+template <typename T, bool INFO, int RPT>
+__global__ void __launch_bounds__(PK_THREADS, 1) k_pcg_persistent(const __grid_constant__ Dev<T> d, const __grid_constant__ PkArgs a, const __grid_constant__ PeerExchange px) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sv = reinterpret_cast<T *>(smem_raw);
+  int *sc = reinterpret_cast<int *>(sv + PK_WARPS * 32 * 9);
+  T *p_s = reinterpret_cast<T *>(sc + PK_WARPS * 32);
+  T *r_s = p_s + RPT * PK_THREADS;
+  T *y_s = r_s + RPT * PK_THREADS;
+  double *red_warp = reinterpret_cast<double *>(y_s + RPT * PK_THREADS);  // [32] + [2] broadcast slots
+  double *bcast = red_warp + 32;
+  const int tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+  const size_t rs = 9 * (size_t)d.nC, set_sz = (size_t)NREP * rs;
+  // camera rows of this CTA: whole cameras
+  const int per = (d.nC + G - 1) / G;
+  const int c0 = min(d.nC, b * per), c1 = min(d.nC, c0 + per);
+  const int i0 = 9 * c0, nrows = 9 * (c1 - c0);
+  const bool timer = b == 0 && tid == 0 && a.timers;
+  // The PCG state lives in shared memory between camera phases (every thread holds an identical copy while it works
+  // on it): 20 registers that would otherwise stay live across the edge phases and push them into spills.
+  __shared__ PcgState st_s;
+  __shared__ unsigned long long epoch_s;
+  if (tid == 0) {
+    PcgState st0;
+    st0.rho = 0.; st0.rho_prev = 0.; st0.rho_min = INFINITY; st0.alpha = 0.; st0.pq = 0.;
+    st0.tol = a.tol; st0.refuse = a.refuse; st0.n = 0; st0.max_iter = a.max_iter > 1 ? a.max_iter : 1; st0.active = 1; st0.done = 0; st0.refused = 0; st0.pad = 0;
+    st_s = st0;
+    epoch_s = px.epoch;
+  }
+  __syncthreads();
+  int pass = 0;
+
+  // camera phase.  INIT: r = g_c - (Hpp x0 - T^T Y), z, rho, p = z.  Otherwise one PCG iteration's camera work.
+  auto camera_phase = [&](const T *sB, bool init) -> bool {
+    PcgState st = st_s;
+    unsigned long long epoch = epoch_s;
+    T hd[RPT][9], hinv[RPT][9], tin[RPT][3], tout[RPT][3], pj[RPT], rj[RPT], xj[RPT], xb[RPT], sj[RPT], qj[RPT], zj[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PK_THREADS;
+      pj[j] = rj[j] = xj[j] = xb[j] = sj[j] = qj[j] = zj[j] = T(0);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) tin[j][m] = tout[j][m] = T(0);
+#pragma unroll
+      for (int m = 0; m < 9; ++m) hd[j][m] = hinv[j][m] = T(0);
+      if (l < nrows) {
+        const int i = i0 + l, c = i / 9, k = i - 9 * c, bk = k / 3, kk = k - 3 * bk;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+          hd[j][m] = __ldg(d.HppD + 81 * (size_t)c + 9 * k + m);
+          hinv[j][m] = __ldg(d.HppInv + 81 * (size_t)c + 9 * k + m);
+        }
+        const T *tb = d.camT + (size_t)CAMT * c + 9 * bk;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          const T rowv = __ldg(tb + 3 * kk + m), colv = __ldg(tb + 3 * m + kk);
+          tin[j][m] = bk == 1 ? colv : rowv;
+          tout[j][m] = bk == 1 ? rowv : colv;
+        }
+        xj[j] = d.dxc[i];
+        T sbv[NREP];
+#pragma unroll
+        for (int rep = 0; rep < NREP; ++rep) sbv[rep] = __ldcg(sB + rep * rs + i);
+        T sb = T(0);
+#pragma unroll
+        for (int rep = 0; rep < NREP; ++rep) sb += sbv[rep];
+        sj[j] = sb;
+        if (init) { pj[j] = xj[j]; rj[j] = d.gc[i]; }
+        else { pj[j] = __ldcg(d.p + i); rj[j] = __ldcg(d.r + i); }
+        p_s[l] = pj[j];
+        if (px.ws > 1) {  // push this rank's partial into every rank's inbox
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r < px.ws) (reinterpret_cast<T *>(px.data[r]) + ((size_t)((int)(epoch & 1) * px.ws + px.rank) * 2) * rs)[i] = sb;
+        }
+      }
+    }
+    if (px.ws > 1) {
+      __threadfence_system();
+      grid.sync();  // every CTA's pushes are ordered before the flags go up
+      const int par = (int)(epoch & 1);
+      if (b == 0 && tid < px.ws)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flag[tid] + par * 8 + px.rank), "l"(epoch) : "memory");
+      if (nrows > 0) {
+        if (tid < px.ws) {
+          const unsigned long long *f = px.flag[px.rank] + par * 8 + tid;
+          unsigned long long v = 0;
+          const long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+          } while (v < epoch && clock64() - t0 < 4000000000ll);
+          if (v < epoch) d.scal[S_XCHG_ERR] = 1.;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int l = tid + j * PK_THREADS;
+          if (l < nrows) {
+            const int i = i0 + l;
+            T pb[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              pb[r] = T(0);
+              if (r < px.ws) pb[r] = __ldcv(reinterpret_cast<const T *>(px.data[px.rank]) + ((size_t)(par * px.ws + r) * 2) * rs + i);
+            }
+            T sb = T(0);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) sb += pb[r];
+            sj[j] = sb;
+          }
+        }
+      }
+      epoch += 1;
+    }
+    // s = T^T Y
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PK_THREADS;
+      if (l < nrows) y_s[l] = sj[j];
+    }
+    __syncthreads();
+    double acc = 0.;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PK_THREADS;
+      if (l < nrows) {
+        const int k = (i0 + l) % 9, lb = l - k % 3, lc = l - k;
+        const T sv_ = tout[j][0] * y_s[lb] + tout[j][1] * y_s[lb + 1] + tout[j][2] * y_s[lb + 2];
+        T aq = T(0);
+#pragma unroll
+        for (int m = 0; m < 9; ++m) aq += hd[j][m] * p_s[lc + m];
+        qj[j] = aq - sv_;                          // q = Hpp p - Hpl Hll^-1 Hlp p  (:359-366)
+        if (init) rj[j] = rj[j] - qj[j];           // r = v - S x0                  (:182-258)
+        else acc += (double)(pj[j] * qj[j]);
+      }
+    }
+    if (!init) {
+      pk_cta_partial(acc, red_warp, a.partials + b);
+      grid.sync();
+      const double pq = pk_total(a.partials, G, bcast);
+      const T alpha = pq != 0. ? (T)(st.rho / pq) : T(0);   // :385
+      st.alpha = (double)alpha; st.pq = pq;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        xb[j] = xj[j];                             // :389
+        xj[j] = xj[j] + alpha * pj[j];             // :391
+        rj[j] = rj[j] + (-alpha) * qj[j];          // :400
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PK_THREADS;
+      if (l < nrows) r_s[l] = rj[j];
+    }
+    __syncthreads();
+    acc = 0.;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PK_THREADS;
+      if (l < nrows) {
+        const int lc = l - (i0 + l) % 9;
+        T az = T(0);
+#pragma unroll
+        for (int m = 0; m < 9; ++m) az += hinv[j][m] * r_s[lc + m];
+        zj[j] = az;                                // z = M^-1 r                    (:273-275)
+        acc += (double)(rj[j] * az);
+      }
+    }
+    pk_cta_partial(acc, red_warp, a.partials + G + b);
+    grid.sync();
+    const double rho_new = (double)(T)pk_total(a.partials + G, G, bcast + 1);  // rhoN is a T in the reference
+    bool cont = true, refused = false;
+    if (!init) {
+      st.n += 1;                                   // :405
+      st.done = fabs(st.rho) < st.tol;             // :406
+      cont = !st.done && st.n < st.max_iter;       // :407
+    }
+    T beta = T(0);
+    if (cont) {
+      if (rho_new > st.refuse * st.rho_min) {      // :288-295
+        st.refused = 1; refused = true; cont = false;
+      } else {
+        st.rho_min = fmin(st.rho_min, rho_new);    // :296
+        if (!init) beta = st.rho != 0. ? (T)(rho_new / st.rho) : T(0);  // :299
+        st.rho_prev = st.rho;
+        st.rho = rho_new;
+      }
+    }
+    st.active = cont ? 1 : 0;
+    __syncthreads();  // p_s is rewritten below
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PK_THREADS;
+      if (l < nrows) {
+        const int i = i0 + l;
+        d.r[i] = rj[j];
+        if (!init) {
+          xj[j] = refused ? xb[j] : xj[j];
+          d.dxc[i] = xj[j];
+          d.xbk[i] = xb[j];
+        }
+        T pv = pj[j];
+        if (cont) {
+          pv = init ? zj[j] : zj[j] + beta * pj[j];  // :310 / :299-306
+          d.p[i] = pv;
+        }
+        // what the next edge phase gathers: T p while the loop continues, T x for the back-substitution after it
+        p_s[l] = cont ? pv : xj[j];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int l = tid + j * PK_THREADS;
+      if (l < nrows) {
+        const int i = i0 + l, lb = l - (i % 9) % 3;
+        d.xpad[(size_t)CamPad<T>::N * (i / 9) + i % 9] = tin[j][0] * p_s[lb] + tin[j][1] * p_s[lb + 1] + tin[j][2] * p_s[lb + 2];
+      }
+    }
+    if (b == 0 && tid == 0) a.counters[(pass + 2) & 3] = 0;  // the counter of the edge phase after the next one
+    __syncthreads();  // every thread has taken its copy of the state
+    if (tid == 0) { st_s = st; epoch_s = epoch; }
+    __syncthreads();
+    return cont;
+  };
+
+  unsigned long long t_a = 0;
+  auto tick = [&](int slot) {  // CTA 0, thread 0: device-timer bookkeeping between grid barriers
+    if (timer) {
+      const unsigned long long t = pk_now();
+      if (slot >= 0) { a.timers[slot] += (double)(t - t_a); a.timers[slot + 1] += 1.; }
+      t_a = t;
+    }
+  };
+
+  // ---- MakeV + S*x0 in one pass (xpad = T x0 was prepared by the host), then the INIT camera phase
+  tick(-1);
+  pk_edge_phase<T, SM_INIT, INFO>(d, a.counters + (pass & 3), d.xpad, d.sB, nullptr, sv, sc);
+  grid.sync();
+  tick(0);
+  bool cont = camera_phase(d.sB, true);
+  pass += 1;
+  grid.sync();
+  tick(2);
+  // ---- the do-while of schur_pcg_solver.cu:265-407
+  int it = 0;
+  while (cont) {
+    T *cur = d.sB + (size_t)((it + 1) & 1) * set_sz, *other = d.sB + (size_t)(it & 1) * set_sz;
+    pk_edge_phase<T, SM_FULL, INFO>(d, a.counters + (pass & 3), d.xpad, cur, other, sv, sc);
+    grid.sync();
+    tick(0);
+    cont = camera_phase(cur, false);
+    pass += 1;
+    it += 1;
+    grid.sync();
+    tick(2);
+  }
+  // ---- back-substitution: dx_l = w - Hll^-1 Hlp dx_c  (xpad holds T dx_c)
+  pk_edge_phase<T, SM_BACKSUB, INFO>(d, a.counters + (pass & 3), d.xpad, nullptr, nullptr, sv, sc);
+  if (b == 0 && tid == 0) *d.st = st_s;
+}
+
+// --------------------------------------------------------------------------------
 // LM scalars: sum (J dx + r)^2 at x and sum r^2 at x + dx in one pass.
 template <typename T>
 __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
@@ -765,6 +1188,53 @@ static cudaError_t launch_schur_ell_m(const Dev<T> &d, int mode, const T *xin, T
   }
 }
 
+// ---- persistent PCG kernel: availability and launch
+static int pk_grid(int *sms_out = nullptr) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms_out) *sms_out = sms;
+  return sms;
+}
+template <typename T, bool INFO, int RPT>
+static cudaError_t launch_pk_v(const Dev<T> &d, const PkArgs &a, const PeerExchange &px, cudaStream_t st) {
+  auto kern = k_pcg_persistent<T, INFO, RPT>;
+  const size_t smem = pk_smem<T>(RPT);
+  static bool prepared_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!prepared_dev[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    prepared_dev[dev & 63] = true;
+  }
+  Dev<T> dd = d;
+  PkArgs aa = a;
+  PeerExchange pxx = px;
+  void *args[] = {&dd, &aa, &pxx};
+  return cudaLaunchCooperativeKernel((void *)kern, dim3(pk_grid()), dim3(PK_THREADS), args, smem, st);
+}
+template <typename T>
+bool pcg_persistent_available(const Dev<T> &d) {
+  if (!d.ell || d.store != ST_FACT || d.no_pdl) return false;  // no_pdl: ranks share the device, a cooperative grid would starve them
+  int dev = 0, coop = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  const int G = pk_grid(&sms);
+  if (!coop || G <= 0) return false;
+  const int per = (d.nC + G - 1) / G;
+  return 9 * per <= 2 * PK_THREADS;
+}
+template <typename T>
+cudaError_t launch_pcg_persistent(const Dev<T> &d, int max_iter, double tol, double refuse, const PeerExchange &px, cudaStream_t st) {
+  PkArgs a{max_iter, tol, refuse, d.pk_counters, d.pk_partials, d.pk_timers};
+  const int G = pk_grid();
+  const int rows = 9 * ((d.nC + G - 1) / G);
+  const bool two = rows > PK_THREADS;
+  if (d.r_info) return two ? launch_pk_v<T, true, 2>(d, a, px, st) : launch_pk_v<T, true, 1>(d, a, px, st);
+  return two ? launch_pk_v<T, false, 2>(d, a, px, st) : launch_pk_v<T, false, 1>(d, a, px, st);
+}
+
 int ell_tma() {
   static int v = -1;
   if (v < 0) { const char *e = getenv("BA_TMA"); v = e ? atoi(e) : 0; }
@@ -857,7 +1327,9 @@ cudaError_t launch_permute3(const T *src, T *dst, const int *perm, int n, int ga
   template cudaError_t launch_trial_ell<T>(const Dev<T> &, cudaStream_t);                                     \
   template cudaError_t launch_eval_edges_ell<T>(const Dev<T> &, T *, T *, cudaStream_t);                      \
   template cudaError_t launch_pad_cam_T<T>(const Dev<T> &, const T *, cudaStream_t);                          \
-  template cudaError_t launch_permute3<T>(const T *, T *, const int *, int, int, cudaStream_t);
+  template cudaError_t launch_permute3<T>(const T *, T *, const int *, int, int, cudaStream_t);                \
+  template bool pcg_persistent_available<T>(const Dev<T> &);                                                  \
+  template cudaError_t launch_pcg_persistent<T>(const Dev<T> &, int, double, double, const PeerExchange &, cudaStream_t);
 BA_INSTANTIATE_ELL(double)
 BA_INSTANTIATE_ELL(float)
 

@@ -126,6 +126,9 @@ struct Dev {
   T *r, *p, *q, *z, *xbk;       // PCG vectors [9nC]
   T *xpad;                      // [nC][CamPad::N] padded copy of the vector the edge kernel gathers
   PcgState *st;
+  int *pk_counters;             // [4] slice counters of the persistent PCG kernel
+  double *pk_partials;          // [2][#SMs] per-CTA partial dot products of the persistent PCG kernel
+  double *pk_timers;            // [4] device-timer sums of the persistent PCG kernel (edge ns, edge phases, camera ns, camera phases)
   double *scal;                 // [S_COUNT]
   double *partials;             // per-CTA partial sums
   double damp;                  // 1/region
@@ -165,6 +168,8 @@ template <typename T> cudaError_t launch_eval_edges_ell(const Dev<T> &d, T *r_sl
 template <typename T> cudaError_t launch_pad_cam_T(const Dev<T> &d, const T *src, cudaStream_t st);
 template <typename T> cudaError_t launch_permute3(const T *src, T *dst, const int *perm, int n, int gather, cudaStream_t st);
 int launches_of_linearize_ell();
+template <typename T> bool pcg_persistent_available(const Dev<T> &d);
+template <typename T> cudaError_t launch_pcg_persistent(const Dev<T> &d, int max_iter, double tol, double refuse, const PeerExchange &px, cudaStream_t st);
 bool pdl_enabled();
 
 }  // namespace ba

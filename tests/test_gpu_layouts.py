@@ -149,3 +149,35 @@ def test_lm_trace_on_bal_like_graph(flavour):
     assert np.allclose([r["cost"] for r in tr], [r["cost"] for r in tr0], rtol=1e-8)
     cam, pt = S.get_params()
     assert rel_fro(np.concatenate([cam.ravel(), pt.ravel()]), x1) <= 1e-7
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["medium", "bal"])
+def test_persistent_pcg_kernel(name, dtype):
+    """ba_set_persistent(1): the whole solve in one cooperative launch (edge phases with dynamic slice scheduling, camera
+    phases spread over all SMs, grid barriers) gives the step of the two-launches-per-iteration path, including the
+    reference's early exits."""
+    P = PROBLEMS[name]()
+    A, B = _solver(P, dtype, "ell-fact"), _solver(P, dtype, "ell-fact")
+    B.set_persistent(True)
+    t = TOL[np.dtype(dtype)]
+    for S in (A, B):
+        S.linearize()
+        S.process_diag(1e3)
+    ita = A.solve(max_iter=12, tol=0.0, refuse_ratio=1e300)
+    itb = B.solve(max_iter=12, tol=0.0, refuse_ratio=1e300)
+    assert ita == itb
+    O, _, dx0, _ = _oracle_step(P, dtype, 1e3, 12)
+    assert rel_fro(B.read(capi.BUF_DX), dx0) <= t["dx"]
+    assert rel_fro(B.read(capi.BUF_DX), A.read(capi.BUF_DX)) <= t["dx"]
+    ita = A.solve(max_iter=100, tol=1e-1, refuse_ratio=1.0)   # warm start + the README stopping rules
+    itb = B.solve(max_iter=100, tol=1e-1, refuse_ratio=1.0)
+    assert ita == itb
+    assert rel_fro(B.read(capi.BUF_DX), A.read(capi.BUF_DX)) <= 10 * t["dx"]
+    kw = dict(lm_max_iter=4, initial_region=1e3, eps1=1e-3, eps2=1e-12, pcg_max_iter=30, pcg_tol=1e-3, pcg_refuse=1.0)
+    A.set_params(P.cam, P.pt)
+    B.set_params(P.cam, P.pt)
+    tra, trb = A.lm_solve(**kw), B.lm_solve(**kw)
+    assert [r["accepted"] for r in tra] == [r["accepted"] for r in trb]
+    assert [r["pcg_iters"] for r in tra] == [r["pcg_iters"] for r in trb]
+    assert np.allclose([r["cost"] for r in tra], [r["cost"] for r in trb], rtol=50 * t["cost"])
