@@ -414,6 +414,9 @@ struct ImplT : Impl {
   T *e_info_dev = nullptr, *cm_info_dev = nullptr;
   T *pt_full = nullptr;  // [3 nP] gather buffer, world_size > 1 only
   void *coll_scratch = nullptr;  // result buffer of the in-process allreduce (>= 90 nC scalars)
+  double *model_part = nullptr;  // [nW] point partials of the model decrease (left by the back-substitution pass)
+  bool model_valid = false;      // scal[S_MODEL_PT / S_MODEL_CAM] describe the step of the last solve
+  double last_cost = 0.;         // F of the current linearisation
   // ELL layout
   int *perm_dev = nullptr; // [nPl] device position -> local point
   T *pt_nat = nullptr;     // [3 nPl] staging in the caller's point order
@@ -426,6 +429,7 @@ struct ImplT : Impl {
   std::vector<size_t> ev_schur, ev_lin, ev_pcg, ev_solve, ev_cam;
   int pcg_chunk = 8;
   int launched = 0;             // PCG iterations enqueued by the current / last solve
+  int last_iters = 1 << 20;     // iterations the previous solve executed
   bool solve_pending = false;   // ba_solve_async enqueued, ba_solve_wait not yet called
   std::vector<std::pair<size_t, int>> loc_schur, loc_cam;  // (event pair, iteration) of the sampled launches
   // fused peer-memory exchange of the camera kernel (world_size > 1)
@@ -611,7 +615,7 @@ struct ImplT : Impl {
     int2 *cdesc = nullptr;
     add(&tile, g.nT); add(&e_cam, nSlots); add(&e_lp, ell ? 0 : nSlots); add(&e_obs, 2 * nSlots); add(&pt_slot, ell ? 0 : nPl);
     if (ell) {
-      add(&wdesc, g.nW); add(&cdesc, g.cdesc.size()); add(&d.camc, (size_t)CAMC * nC); add(&d.camT, (size_t)CAMT * nC);
+      add(&wdesc, g.nW); add(&cdesc, g.cdesc.size()); add(&d.camc, (size_t)CAMC * nC); add(&d.camc2, (size_t)CAMC * nC); add(&d.camT, (size_t)CAMT * nC);
       add(&d.HllInvP, 9 * nPlPad); add(&d.wP, 3 * nPlPad); add(&d.XP, 3 * nPlPad);
       add(&perm_dev, nPl); add(&pt_nat, 3 * nPl);
     }
@@ -628,6 +632,7 @@ struct ImplT : Impl {
     add(&d.xpad, (size_t)CamPad<T>::N * nC);
     add(&d.st, 1); add(&d.scal, S_COUNT); add(&d.partials, nPart);
     add(&d.pk_counters, 4); add(&d.pk_partials, 2 * 512); add(&d.pk_timers, 4);
+    add(&model_part, std::max<size_t>(g.nW, 1));
     size_t total = 0;
     for (auto &it : items) total += (it.bytes + 255) / 256 * 256 + 256;
     BA_CUDA(cudaMalloc(&arena, total));
@@ -903,6 +908,7 @@ struct ImplT : Impl {
     BA_TRY(fetch_scalars());
     ginf_valid = fuse_ginf;
     if (cost) *cost = h_scal[S_COST];
+    last_cost = h_scal[S_COST];
     // a camera in the small-angle branch (theta^2 <= eps) makes this linearisation stream the Jacobian instead
     if (g.ell) d.store = (store_cfg == ST_FACT && h_scal[S_ANY_SMALL] == 0.) ? ST_FACT : ST_J;
     linearized = true;
@@ -996,6 +1002,7 @@ struct ImplT : Impl {
       BA_CUDA(launch_pcg_persistent<T>(d, max_iter, o->tol, o->refuse_ratio, pxl, stream));
       if (timing) { ev_end(ev_p); ev_pcg.push_back(ev_p); ev_end(ev_s); ev_solve.push_back(ev_s); }
       stats.launches += 1;
+      model_valid = false;
       launched = 0;
       loc_schur.clear();
       loc_cam.clear();
@@ -1033,8 +1040,11 @@ struct ImplT : Impl {
       if (!hs.active) finished = true;
       return BA_OK;
     };
+    // first chunk: what the previous solve needed (+1), so that a loop that exits after two or three iterations
+    // (README tolerances) is not followed by a tail of no-op launches; later chunks: pcg_chunk
+    const int first_chunk = std::max(2, std::min(pcg_chunk, last_iters + 1));
     while (launched < max_iter && !finished) {
-      const int n = std::min(pcg_chunk, max_iter - launched);
+      const int n = std::min(launched == 0 ? first_chunk : pcg_chunk, max_iter - launched);
       for (int i = 0; i < n; ++i) {
         // iteration it accumulates into set (it+1)&1 and clears set it&1 (read by the previous camera kernel)
         const int it = launched + i;
@@ -1069,7 +1079,22 @@ struct ImplT : Impl {
     // for them: launches past the end of the loop are no-ops, so one host round trip at the very end fetches the final
     // PCG state and the scalars together.
     BA_TRY(pad_cam(d.dxc));
+    // Without information matrices H = J^T J exactly, so the model decrease ||J dx + r||^2 - ||r||^2 of the trial step
+    // is  dx^T H dx - 2 g^T dx : the back-substitution pass has Hlp dx_c per point in hand and leaves the point part,
+    // a one-block kernel adds the camera part -- ba_eval_trial then only needs the trial cost.
+    static const bool model_env = !(getenv("BA_MODEL_QUAD") && atoi(getenv("BA_MODEL_QUAD")) == 0);
+    const bool quad = g.ell && d.store == ST_FACT && !d.r_info && model_env && fuse_norms;
+    d.model_partials = quad ? model_part : nullptr;
     BA_TRY(schur_edge(SM_BACKSUB, d.xpad, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
+    d.model_partials = nullptr;
+    if (quad) {
+      Dev<T> dm = d;
+      dm.model_partials = model_part;
+      BA_CUDA(launch_model_terms<T>(dm, stream));
+      stats.launches += 2;
+      BA_TRY(allreduce_scal(S_MODEL_PT, 1, ncclSum));
+    }
+    model_valid = quad;
     if (timing) { ev_end(ev_s); ev_solve.push_back(ev_s); }
     if (fuse_norms) {
       BA_CUDA(launch_norms<T>(d, stream));
@@ -1109,6 +1134,7 @@ struct ImplT : Impl {
     for (auto &e : loc_schur) if (e.second < h_st[0].n) ev_schur.push_back(e.first);
     for (auto &e : loc_cam) if (e.second < h_st[0].n) ev_cam.push_back(e.first);
     stats.pcg_iters += h_st[0].n;
+    last_iters = h_st[0].n;
     if (iters) *iters = h_st[0].n;
     if (done) *done = h_st[0].done;
     return BA_OK;
@@ -1130,8 +1156,24 @@ struct ImplT : Impl {
 
   int eval_trial(double *cost_new, double *model_sq) override {
     BA_CUDA(cudaSetDevice(opt.device));
-    if (g.ell) BA_CUDA(launch_trial_ell<T>(d, stream));
-    else BA_CUDA(launch_trial<T>(d, stream));
+    if (g.ell && model_valid && d.store == ST_FACT) {
+      // the model term came with the solve (see solve_enqueue); only the trial cost needs the observations
+      model_valid = false;
+      const double msq = last_cost + h_scal[S_MODEL_PT] + h_scal[S_MODEL_CAM];
+      BA_CUDA(launch_trial_cost_ell<T>(d, stream));
+      stats.launches += 3;
+      BA_TRY(allreduce_scal(S_TRIAL_COST, 1, ncclSum));
+      BA_TRY(fetch_scalars());
+      if (cost_new) *cost_new = h_scal[S_TRIAL_COST];
+      if (model_sq) *model_sq = msq;
+      return BA_OK;
+    }
+    if (g.ell) {
+      if (d.store == ST_FACT) BA_TRY(pad_cam(d.dxc));  // the factored trial kernel gathers T_c dx_c
+      BA_CUDA(launch_trial_ell<T>(d, stream));
+    } else {
+      BA_CUDA(launch_trial<T>(d, stream));
+    }
     stats.launches += 2;
     BA_TRY(allreduce_scal(S_TRIAL_COST, 2, ncclSum));
     BA_TRY(fetch_scalars());

@@ -50,6 +50,22 @@ __device__ __forceinline__ void load_camc(const T *__restrict__ camc, int c, T *
   rc.small = v[14] != T(0);
 }
 
+// the first 12 scalars of a row only (cam[9], c, a, b): all a kernel needs that runs when no camera is in the
+// small-angle branch and evaluates no rotation derivative (6 instead of 8 sixteen-byte gathers per observation)
+template <typename T>
+__device__ __forceinline__ void load_camc_lite(const T *__restrict__ camc, int c, T *cm, RotConst<T> &rc) {
+  using V = typename CamPad<T>::vec;
+  constexpr int NV = 12 * sizeof(T) / 16;
+  __align__(16) T v[12];
+  const V *src = reinterpret_cast<const V *>(camc + (size_t)CAMC * c);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) reinterpret_cast<V *>(v)[k] = __ldg(src + k);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cm[k] = v[k];
+  rc.c = v[9]; rc.a = v[10]; rc.b = v[11]; rc.ap = T(0); rc.bp = T(0);
+  rc.small = false;  // for a small-angle camera c = a = 1, b = 0 reproduce the first-order branch exactly
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) k_cam_consts(Dev<T> d) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,7 +147,8 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
     if (c < 0) continue;
     T cm[9];
     RotConst<T> rc;
-    load_camc<T>(d.camc, c, cm, rc);
+    if (STORE == ST_FACT) load_camc_lite<T>(d.camc, c, cm, rc);  // this flavour only runs without small-angle cameras
+    else load_camc<T>(d.camc, c, cm, rc);
     const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
     T r0, r1, Jp[6];
     if (STORE == ST_FACT) {
@@ -387,10 +404,29 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
   T u2 = hi[6] * t0 + hi[7] * t1 + hi[8] * t2;
   if (MODE == SM_INIT) { u0 -= wv[0]; u1 -= wv[1]; u2 -= wv[2]; }  // u = Hll^-1 Hlp x0 - w: one pass yields Hpl Hll^-1 Hlp x0 - Hpl w
   if (MODE == SM_BACKSUB) {
-    if (pvalid && (!wd.heavy || lane == 0)) {
-      d.dxl[3 * (size_t)p] = wv[0] - u0;
-      d.dxl[3 * (size_t)p + 1] = wv[1] - u1;
-      d.dxl[3 * (size_t)p + 2] = wv[2] - u2;
+    const T l0 = wv[0] - u0, l1 = wv[1] - u1, l2 = wv[2] - u2;
+    const bool owner = pvalid && (!wd.heavy || lane == 0);
+    if (owner) {
+      d.dxl[3 * (size_t)p] = l0;
+      d.dxl[3 * (size_t)p + 1] = l1;
+      d.dxl[3 * (size_t)p + 2] = l2;
+    }
+    if (d.model_partials) {
+      // point part of  ||J dx + r||^2 - ||r||^2 = dx^T (J^T J) dx - 2 g^T dx  (computeRhoDenominator, lm_algo.cu:61-126,
+      // without a pass over the observations): dx_l^T Hll dx_l + 2 (Hlp dx_c)^T dx_l - 2 g_l^T dx_l; t = Hlp dx_c is in hand
+      double m = 0.;
+      if (owner) {
+        T h[9], gv[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) h[k] = d.Hll[9 * (size_t)p + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gv[k] = d.gl[3 * (size_t)p + k];
+        const T q0 = h[0] * l0 + h[1] * l1 + h[2] * l2, q1 = h[3] * l0 + h[4] * l1 + h[5] * l2, q2 = h[6] * l0 + h[7] * l1 + h[8] * l2;
+        m = (double)(l0 * q0 + l1 * q1 + l2 * q2) + 2. * (double)(t0 * l0 + t1 * l1 + t2 * l2) -
+            2. * (double)(gv[0] * l0 + gv[1] * l1 + gv[2] * l2);
+      }
+      m = warp_sum<double>(m);
+      if (lane == 0) d.model_partials[w] = m;
     }
     return;
   }
@@ -1037,6 +1073,244 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
   }
 }
 
+// --------------------------------------------------------------------------------
+// HP1 on the factored stream.  With J~ = [X x Jp_i | Jp_i | B_i (1, l2, l2^2)] (2 x 9) the camera block is Jc = J~ T_c,
+// so   Hpp_c = T_c^T (sum_e J~^T Omega J~) T_c   and   g_c = -T_c^T sum_e J~^T Omega r:
+// the camera-major pass needs r, Jp and B only (no rotation derivatives), and T_c is applied once per camera.
+template <typename T, bool INFO>
+__global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm_fact(Dev<T> d) {
+  if (d.scal[S_ANY_SMALL] != 0.) return;  // a small-angle camera: k_lin_cm does the work (device-side dispatch)
+  constexpr int NW = CM_THREADS / 32;
+  __shared__ T sh[NW][NTRI + 9];
+  const int4 ch = d.chunk[blockIdx.x];
+  const int c = ch.x, beg = ch.y, end = ch.z;
+  T cm[9];
+  RotConst<T> rc;
+  load_camc_lite<T>(d.camc, c, cm, rc);
+  T acc[NTRI + 9];
+#pragma unroll
+  for (int k = 0; k < NTRI + 9; ++k) acc[k] = T(0);
+  for (int k = beg + (int)threadIdx.x; k < end; k += CM_THREADS) {
+    const int p = d.cm_pt[k];
+    const T X0 = d.pt[3 * (size_t)p], X1 = d.pt[3 * (size_t)p + 1], X2 = d.pt[3 * (size_t)p + 2];
+    const typename Vec2<T>::type ob = reinterpret_cast<const typename Vec2<T>::type *>(d.cm_obs)[k];
+    T r0, r1, Jp[6], B0, B1;
+    edge_point_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, Jp, B0, B1);
+    const T l2 = B0 * B0 + B1 * B1, l4 = l2 * l2;
+    T Jt[18];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const T a0 = Jp[3 * i], a1 = Jp[3 * i + 1], a2 = Jp[3 * i + 2], Bi = i == 0 ? B0 : B1;
+      Jt[9 * i] = X1 * a2 - X2 * a1;
+      Jt[9 * i + 1] = X2 * a0 - X0 * a2;
+      Jt[9 * i + 2] = X0 * a1 - X1 * a0;
+      Jt[9 * i + 3] = a0; Jt[9 * i + 4] = a1; Jt[9 * i + 5] = a2;
+      Jt[9 * i + 6] = Bi; Jt[9 * i + 7] = Bi * l2; Jt[9 * i + 8] = Bi * l4;
+    }
+    T Lb[18];
+    const T *L = Jt;
+    if (INFO) {
+      T om[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) om[q] = d.cm_info[4 * (size_t)k + q];
+#pragma unroll
+      for (int y = 0; y < 9; ++y) {
+        Lb[y] = Jt[y] * om[0] + Jt[9 + y] * om[2];
+        Lb[9 + y] = Jt[y] * om[1] + Jt[9 + y] * om[3];
+      }
+      L = Lb;
+    }
+    int idx = 0;
+#pragma unroll
+    for (int y = 0; y < 9; ++y) {
+#pragma unroll
+      for (int i = y; i < 9; ++i) acc[idx++] += L[y] * Jt[i] + L[9 + y] * Jt[9 + i];
+      acc[NTRI + y] -= L[y] * r0 + L[9 + y] * r1;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NTRI + 9; ++k) {
+    const T v = warp_sum<T>(acc[k]);
+    if (lane == 0) sh[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NTRI + 9) {
+    T v = T(0);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += sh[w][threadIdx.x];
+    d.cm_part[(size_t)blockIdx.x * (NTRI + 9) + threadIdx.x] = v;
+  }
+}
+
+// element (i, a) of the block-diagonal T_c (blocks Jr, R^T, E; stored Jr, R, E row-major)
+template <typename T>
+__device__ __forceinline__ T camT_el(const T *tb, int i, int a) {
+  const int bk = i / 3;
+  if (bk != a / 3) return T(0);
+  const int ii = i - 3 * bk, aa = a - 3 * bk;
+  return bk == 1 ? tb[9 + 3 * aa + ii] : tb[9 * bk + 3 * ii + aa];
+}
+
+// chunk partials (fixed order) -> H~ (symmetric 9x9), g~ -> Hpp = T^T H~ T, g_c = T^T g~
+template <typename T>
+__global__ void __launch_bounds__(96) k_lin_cam_reduce_fact(Dev<T> d) {
+  if (d.scal[S_ANY_SMALL] != 0.) return;
+  __shared__ T Hs[81], gs[9], Ts[CAMT];
+  const int c = blockIdx.x, k = threadIdx.x;
+  if (k < NTRI + 9) {
+    T v = T(0);
+    for (int ch = d.cam_chunk_ptr[c]; ch < d.cam_chunk_ptr[c + 1]; ++ch) v += d.cm_part[(size_t)ch * (NTRI + 9) + k];
+    if (k >= NTRI) {
+      gs[k - NTRI] = v;
+    } else {
+      int y = 0, rem = k;
+      while (rem >= 9 - y) { rem -= 9 - y; ++y; }
+      const int i = y + rem;
+      Hs[9 * y + i] = v;
+      Hs[9 * i + y] = v;
+    }
+  }
+  if (k < CAMT) Ts[k] = d.camT[(size_t)CAMT * c + k];
+  __syncthreads();
+  if (k < 81) {
+    int a = k / 9, b = k - 9 * a;
+    if (a > b) { const int t = a; a = b; b = t; }  // both mirror entries evaluate the same expression: exact symmetry
+    const int ba = 3 * (a / 3), bb = 3 * (b / 3);
+    T v = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      T w = T(0);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) w += Hs[9 * (ba + i) + bb + j] * camT_el<T>(Ts, bb + j, b);
+      v += camT_el<T>(Ts, ba + i, a) * w;
+    }
+    d.Hpp[81 * (size_t)c + k] = v;
+  } else if (k < 90) {
+    const int a = k - 81, ba = 3 * (a / 3);
+    T v = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v += camT_el<T>(Ts, ba + i, a) * gs[ba + i];
+    d.gc[9 * (size_t)c + a] = v;
+  }
+}
+
+// rotation constants of the TRIAL cameras cam + dx_c (what k_trial_fact gathers)
+template <typename T>
+__global__ void __launch_bounds__(128) k_cam_consts_trial(Dev<T> d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.nC) return;
+  T cm[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cm[k] = d.cam[9 * (size_t)c + k] + d.dxc[9 * (size_t)c + k];  // updateDeltaXTwoVertices, update.cu:14-41
+  const RotConst<T> rc = rot_const<T>(cm[0], cm[1], cm[2]);
+  T *o = d.camc2 + (size_t)CAMC * c;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) o[k] = cm[k];
+  o[9] = rc.c; o[10] = rc.a; o[11] = rc.b; o[12] = rc.ap; o[13] = rc.bp;
+  o[14] = rc.small ? T(1) : T(0);
+  o[15] = T(0);
+}
+
+// LM scalars on the factored stream: J dx = Jp (psi x X + xt + D) + B poly(e) with (psi, xt, e) = T_c dx_c (xpad),
+// r from the stored B; the trial residual from the per-camera trial constants.  No Jacobian, no sincos per observation.
+template <typename T>
+__global__ void __launch_bounds__(ELL_THREADS) k_trial_fact(Dev<T> d) {
+  const int lane = threadIdx.x & 31, w = blockIdx.x * ELL_WARPS + (threadIdx.x >> 5);
+  if (w >= d.nW) return;
+  const WDesc wd = load_desc(d.wdesc, w);
+  const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
+  const bool pvalid = wd.heavy || lane < wd.np;
+  T X0 = T(0), X1 = T(0), X2 = T(0), D0 = T(0), D1 = T(0), D2 = T(0);
+  if (pvalid) {
+    X0 = d.pt[3 * (size_t)p]; X1 = d.pt[3 * (size_t)p + 1]; X2 = d.pt[3 * (size_t)p + 2];
+    D0 = d.dxl[3 * (size_t)p]; D1 = d.dxl[3 * (size_t)p + 1]; D2 = d.dxl[3 * (size_t)p + 2];
+  }
+  double a_model = 0., a_cost = 0.;
+#pragma unroll 2
+  for (int r = 0; r < wd.D; ++r) {
+    const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    T s[8];
+    load_stream<T, 8>(d.WJ, row, lane, s);
+    if (c < 0) continue;
+    const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
+    __align__(16) T g[CamPad<T>::N];
+    gather_cam<T, true>(d.xpad, c, g);
+    const T f = __ldg(d.camc + (size_t)CAMC * c + 6), k1 = __ldg(d.camc + (size_t)CAMC * c + 7), k2 = __ldg(d.camc + (size_t)CAMC * c + 8);
+    const T l2 = s[6] * s[6] + s[7] * s[7];
+    const T fr = f * (T(1) + k1 * l2 + k2 * l2 * l2);
+    const T r0 = fr * s[6] - ob.x, r1 = fr * s[7] - ob.y;  // the residual the linearisation saw (same arithmetic)
+    const T q0 = g[1] * X2 - g[2] * X1 + g[3] + D0;
+    const T q1 = g[2] * X0 - g[0] * X2 + g[4] + D1;
+    const T q2 = g[0] * X1 - g[1] * X0 + g[5] + D2;
+    const T poly = g[6] + l2 * (g[7] + l2 * g[8]);
+    const T m0 = s[0] * q0 + s[1] * q1 + s[2] * q2 + s[6] * poly;
+    const T m1 = s[3] * q0 + s[4] * q1 + s[5] * q2 + s[7] * poly;
+    a_model += (double)((m0 + r0) * (m0 + r0)) + (double)((m1 + r1) * (m1 + r1));
+    T cm[9];
+    RotConst<T> rc;
+    load_camc_lite<T>(d.camc2, c, cm, rc);
+    T s0, s1;
+    edge_residual<T>(cm, rc, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1);
+    a_cost += (double)(s0 * s0) + (double)(s1 * s1);
+  }
+  a_cost = warp_sum<double>(a_cost);
+  a_model = warp_sum<double>(a_model);
+  if (lane == 0) {
+    d.partials[2 * (size_t)w] = a_cost;
+    d.partials[2 * (size_t)w + 1] = a_model;
+  }
+}
+
+// camera part of the model decrease: dx_c^T Hpp dx_c - 2 g_c^T dx_c (one block, fixed order)
+template <typename T>
+__global__ void __launch_bounds__(1024) k_model_cam(Dev<T> d) {
+  __shared__ double red[32];
+  double a = 0.;
+  for (int i = threadIdx.x; i < 9 * d.nC; i += blockDim.x) {
+    const int c = i / 9, k = i - 9 * c;
+    T q = T(0);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) q += d.Hpp[81 * (size_t)c + 9 * k + j] * d.dxc[9 * c + j];
+    a += (double)(d.dxc[i] * q) - 2. * (double)(d.gc[i] * d.dxc[i]);
+  }
+  a = block_sum<double>(a, red);
+  if (threadIdx.x == 0) d.scal[S_MODEL_CAM] = a;
+}
+
+// trial cost only: sum r(x + dx)^2 from the per-camera trial constants
+template <typename T>
+__global__ void __launch_bounds__(ELL_THREADS) k_trial_cost(Dev<T> d) {
+  const int lane = threadIdx.x & 31, w = blockIdx.x * ELL_WARPS + (threadIdx.x >> 5);
+  if (w >= d.nW) return;
+  const WDesc wd = load_desc(d.wdesc, w);
+  const int p = wd.heavy ? wd.pt0 : wd.pt0 + lane;
+  const bool pvalid = wd.heavy || lane < wd.np;
+  T X0 = T(0), X1 = T(0), X2 = T(0);
+  if (pvalid) {
+    X0 = d.pt[3 * (size_t)p] + d.dxl[3 * (size_t)p];
+    X1 = d.pt[3 * (size_t)p + 1] + d.dxl[3 * (size_t)p + 1];
+    X2 = d.pt[3 * (size_t)p + 2] + d.dxl[3 * (size_t)p + 2];
+  }
+  double a_cost = 0.;
+#pragma unroll 2
+  for (int r = 0; r < wd.D; ++r) {
+    const size_t slot = ((size_t)wd.row0 + r) * 32 + lane;
+    const int c = __ldg(d.r_cam + slot);
+    if (c < 0) continue;
+    const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
+    T cm[9];
+    RotConst<T> rc;
+    load_camc_lite<T>(d.camc2, c, cm, rc);
+    T s0, s1;
+    edge_residual<T>(cm, rc, X0, X1, X2, ob.x, ob.y, s0, s1);
+    a_cost += (double)(s0 * s0) + (double)(s1 * s1);
+  }
+  a_cost = warp_sum<double>(a_cost);
+  if (lane == 0) d.partials[w] = a_cost;
+}
+
 // debug / parity: r[slot][2], J[slot][24]
 template <typename T>
 __global__ void __launch_bounds__(ELL_THREADS) k_eval_edges_ell(Dev<T> d, T *r_out, T *J_out) {
@@ -1112,6 +1386,12 @@ static void launch_lin_ell_s(const Dev<T> &d, int dispatch, cudaStream_t st) {
 
 // d.store is the CONFIGURED store here: ST_FACT launches both point-side flavours (device-side dispatch on the
 // small-angle flag written by k_cam_consts), ST_J only the Jacobian flavour.
+int ell_hp1_fact() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("BA_HP1_FACT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 template <typename T>
 cudaError_t launch_linearize_ell(const Dev<T> &d, cudaStream_t st) {
   if (d.nW > 0) {
@@ -1122,12 +1402,23 @@ cudaError_t launch_linearize_ell(const Dev<T> &d, cudaStream_t st) {
       launch_lin_ell_s<T, ST_J>(d, 0, st);
     }
   }
-  cudaError_t e = launch_lin_cm<T>(d, st);
-  if (e != cudaSuccess) return e;
+  if (d.store == ST_FACT && ell_hp1_fact()) {
+    // both camera-major flavours are launched; the small-angle flag decides on the device which one works
+    if (d.nChunks > 0) {
+      if (d.cm_info) k_lin_cm_fact<T, true><<<d.nChunks, CM_THREADS, 0, st>>>(d);
+      else k_lin_cm_fact<T, false><<<d.nChunks, CM_THREADS, 0, st>>>(d);
+    }
+    k_lin_cam_reduce_fact<T><<<d.nC, 96, 0, st>>>(d);
+    cudaError_t e = launch_lin_cm<T>(d, st, 2);
+    if (e != cudaSuccess) return e;
+  } else {
+    cudaError_t e = launch_lin_cm<T>(d, st, 0);
+    if (e != cudaSuccess) return e;
+  }
   k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nW, 1, d.scal + S_COST);
   return cudaGetLastError();
 }
-int launches_of_linearize_ell() { return 5; }
+int launches_of_linearize_ell() { return 7; }
 
 int ell_rc() {
   static int v = -1;
@@ -1296,8 +1587,26 @@ cudaError_t launch_prep_ell(const Dev<T> &d, cudaStream_t st) {
 
 template <typename T>
 cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st) {
-  if (d.nW > 0) k_trial_ell<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+  if (d.store == ST_FACT && ell_hp1_fact()) {  // d.store = the stream in effect; xpad must hold T_c dx_c (host: pad_cam)
+    k_cam_consts_trial<T><<<(d.nC + 127) / 128, 128, 0, st>>>(d);
+    if (d.nW > 0) k_trial_fact<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+  } else if (d.nW > 0) k_trial_ell<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
   k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nW, 2, d.scal + S_TRIAL_COST);
+  return cudaGetLastError();
+}
+
+// after the back-substitution left the point partials: scal[S_MODEL_PT], scal[S_MODEL_CAM]
+template <typename T>
+cudaError_t launch_model_terms(const Dev<T> &d, cudaStream_t st) {
+  k_reduce<0><<<1, 1024, 0, st>>>(d.model_partials, d.nW, 1, d.scal + S_MODEL_PT);
+  k_model_cam<T><<<1, 1024, 0, st>>>(d);
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_trial_cost_ell(const Dev<T> &d, cudaStream_t st) {
+  k_cam_consts_trial<T><<<(d.nC + 127) / 128, 128, 0, st>>>(d);
+  if (d.nW > 0) k_trial_cost<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+  k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nW, 1, d.scal + S_TRIAL_COST);
   return cudaGetLastError();
 }
 
@@ -1325,6 +1634,8 @@ cudaError_t launch_permute3(const T *src, T *dst, const int *perm, int n, int ga
   template cudaError_t launch_schur_ell<T>(const Dev<T> &, int, const T *, T *, T *, int, cudaStream_t);      \
   template cudaError_t launch_prep_ell<T>(const Dev<T> &, cudaStream_t);                                      \
   template cudaError_t launch_trial_ell<T>(const Dev<T> &, cudaStream_t);                                     \
+  template cudaError_t launch_trial_cost_ell<T>(const Dev<T> &, cudaStream_t);                                \
+  template cudaError_t launch_model_terms<T>(const Dev<T> &, cudaStream_t);                                   \
   template cudaError_t launch_eval_edges_ell<T>(const Dev<T> &, T *, T *, cudaStream_t);                      \
   template cudaError_t launch_pad_cam_T<T>(const Dev<T> &, const T *, cudaStream_t);                          \
   template cudaError_t launch_permute3<T>(const T *, T *, const int *, int, int, cudaStream_t);                \

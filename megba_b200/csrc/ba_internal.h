@@ -76,7 +76,7 @@ struct PeerExchange {
 
 // device scalar slots (double) read back by the host
 enum Scal { S_COST = 0, S_TRIAL_COST = 1, S_MODEL_SQ = 2, S_DX2_PT = 3, S_X2_PT = 4, S_DX2_CAM = 5,
-            S_X2_CAM = 6, S_GINF = 7, S_ANY_SMALL = 8, S_XCHG_ERR = 15, S_COUNT = 16 };
+            S_X2_CAM = 6, S_GINF = 7, S_ANY_SMALL = 8, S_MODEL_PT = 9, S_MODEL_CAM = 10, S_XCHG_ERR = 15, S_COUNT = 16 };
 
 template <typename T>
 struct Dev {
@@ -100,6 +100,7 @@ struct Dev {
   const T *r_obs;               // [nRows][32][2]
   const T *r_info;              // [nRows][32][4] or nullptr
   T *camc;                      // [nC][CAMC]
+  T *camc2;                     // [nC][CAMC] the same for the trial cameras cam + dx_c
   T *camT;                      // [nC][CAMT]
   T *HllInvP, *wP, *XP;         // planes [9][nPlPad], [3][nPlPad], [3][nPlPad] (device order)
   // camera-major static graph
@@ -131,12 +132,14 @@ struct Dev {
   double *pk_timers;            // [4] device-timer sums of the persistent PCG kernel (edge ns, edge phases, camera ns, camera phases)
   double *scal;                 // [S_COUNT]
   double *partials;             // per-CTA partial sums
+  double *model_partials;       // [nW] or nullptr: the back-substitution pass also leaves the point part of the model
+                                // decrease  dx^T H dx - 2 g^T dx  there (computeRhoDenominator without an edge pass)
   double damp;                  // 1/region
 };
 
 // ---- launchers (ba_kernels.cu); all enqueue on `st` and return cudaGetLastError ----
 template <typename T> cudaError_t launch_linearize(const Dev<T> &d, cudaStream_t st);
-template <typename T> cudaError_t launch_lin_cm(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_lin_cm(const Dev<T> &d, cudaStream_t st, int dispatch);
 enum SchurMode { SM_FULL = 0, SM_MAKEV = 1, SM_BACKSUB = 2, SM_INIT = 3 };
 template <typename T> cudaError_t launch_schur_edge(const Dev<T> &d, int mode, const T *xin, T *sout, T *zero_set,
                                                     int check_active, cudaStream_t st);
@@ -164,6 +167,8 @@ template <typename T> cudaError_t launch_schur_ell(const Dev<T> &d, int mode, co
                                                    int check_active, cudaStream_t st);
 template <typename T> cudaError_t launch_prep_ell(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_trial_cost_ell(const Dev<T> &d, cudaStream_t st);
+template <typename T> cudaError_t launch_model_terms(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_eval_edges_ell(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st);
 template <typename T> cudaError_t launch_pad_cam_T(const Dev<T> &d, const T *src, cudaStream_t st);
 template <typename T> cudaError_t launch_permute3(const T *src, T *dst, const int *perm, int n, int gather, cudaStream_t st);

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(TE, 3) k_lin_pm(Dev<T> d) {
 // (camera, chunk of <= CM_CHUNK edges); residual/Jacobian are recomputed from the
 // L2-resident point array instead of being re-read from HBM.
 template <typename T>
-__global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm(Dev<T> d) {
+__global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm(Dev<T> d, int dispatch) {
+  if (dispatch == 2 && d.scal[S_ANY_SMALL] == 0.) return;  // the factored flavour (ba_ell.cu) did the work
   constexpr int NW = CM_THREADS / 32;
   __shared__ T sh[NW][NTRI + 9];
   const int4 ch = d.chunk[blockIdx.x];
@@ -219,7 +220,8 @@ __global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm(Dev<T> d) {
 
 // Sum the chunk partials of one camera (fixed order) and expand the triangle.
 template <typename T>
-__global__ void __launch_bounds__(64) k_lin_cam_reduce(Dev<T> d) {
+__global__ void __launch_bounds__(64) k_lin_cam_reduce(Dev<T> d, int dispatch) {
+  if (dispatch == 2 && d.scal[S_ANY_SMALL] == 0.) return;
   const int c = blockIdx.x, k = threadIdx.x;
   if (k >= NTRI + 9) return;
   T v = T(0);
@@ -1163,9 +1165,9 @@ __global__ void __launch_bounds__(256) k_cam_matvec_sub(Dev<T> d, const T *p, co
 // launchers
 // camera side of the linearisation (layout-independent: it walks the camera-major view)
 template <typename T>
-cudaError_t launch_lin_cm(const Dev<T> &d, cudaStream_t st) {
-  if (d.nChunks > 0) k_lin_cm<T><<<d.nChunks, CM_THREADS, 0, st>>>(d);
-  k_lin_cam_reduce<T><<<d.nC, 64, 0, st>>>(d);
+cudaError_t launch_lin_cm(const Dev<T> &d, cudaStream_t st, int dispatch) {
+  if (d.nChunks > 0) k_lin_cm<T><<<d.nChunks, CM_THREADS, 0, st>>>(d, dispatch);
+  k_lin_cam_reduce<T><<<d.nC, 64, 0, st>>>(d, dispatch);
   return cudaGetLastError();
 }
 
@@ -1175,7 +1177,7 @@ cudaError_t launch_linearize(const Dev<T> &d, cudaStream_t st) {
     if (d.implicit) k_lin_pm<T, true><<<d.nT, TE, 0, st>>>(d);
     else k_lin_pm<T, false><<<d.nT, TE, 0, st>>>(d);
   }
-  launch_lin_cm<T>(d, st);
+  launch_lin_cm<T>(d, st, 0);
   k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nT, 1, d.scal + S_COST);
   return cudaGetLastError();
 }
@@ -1476,7 +1478,7 @@ template cudaError_t launch_sum_ranks<float>(float *, const void *const *, int, 
 
 #define BA_INSTANTIATE(T)                                                                                   \
   template cudaError_t launch_linearize<T>(const Dev<T> &, cudaStream_t);                                   \
-  template cudaError_t launch_lin_cm<T>(const Dev<T> &, cudaStream_t);                                      \
+  template cudaError_t launch_lin_cm<T>(const Dev<T> &, cudaStream_t, int);                                      \
   template cudaError_t launch_schur_edge<T>(const Dev<T> &, int, const T *, T *, T *, int, cudaStream_t);   \
   template cudaError_t launch_prep<T>(const Dev<T> &, cudaStream_t);                                        \
   template cudaError_t launch_pcg_init<T>(const Dev<T> &, T *, int, double, double, int, const PeerExchange &, cudaStream_t); \

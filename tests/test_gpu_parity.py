@@ -238,6 +238,11 @@ def test_lm_trace_matches_oracle(dtype, implicit):
         assert abs(tr[i]["cost"] - tr0[i]["cost"]) <= 10 * t * tr0[i]["cost"], (i, tr[i], tr0[i])
         if dtype == np.float64:
             assert tr[i]["pcg_iters"] == tr0[i]["pcg_iters"], (i, tr[i], tr0[i])
+            # gain ratio and trust region (lm_algo.cu:181-198): inside ba_lm_solve the model decrease comes from the
+            # quadratic form dx^T H dx - 2 g^T dx evaluated in the back-substitution pass, not from an edge pass
+            if i > 0:
+                assert abs(tr[i]["rho"] - tr0[i]["rho"]) <= 1e-6 * max(1.0, abs(tr0[i]["rho"])), (i, tr[i], tr0[i])
+                assert abs(tr[i]["region"] - tr0[i]["region"]) <= 1e-5 * tr0[i]["region"], (i, tr[i], tr0[i])
     if dtype == np.float64:
         cam, pt = S.get_params()
         assert rel_fro(np.concatenate([cam.ravel(), pt.ravel()]), x0) <= 1e-6
