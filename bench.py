@@ -48,12 +48,23 @@ def physical_cores():
 
 
 # The CPU arms (oracle port) run on all physical cores with threads pinned, whatever the launcher exported
-# (torch.distributed.run sets OMP_NUM_THREADS=1).  libgomp reads these once, when the first OpenMP library loads.
+# (torch.distributed.run sets OMP_NUM_THREADS=1).  libgomp reads these once, when the first OpenMP library loads, and
+# OMP_PROC_BIND also pins the process's MAIN thread -- so they are set only in a process that runs nothing but a CPU arm
+# (`--impl reference`, or the child process the GPU arm spawns for its cpu_baseline).  Setting them in the GPU ranks
+# would pin every rank's launching thread onto the same core.
 CPU_THREADS = physical_cores()
-os.environ["OMP_NUM_THREADS"] = str(CPU_THREADS)
-os.environ["OMP_PROC_BIND"] = "close"
-os.environ["OMP_PLACES"] = "cores"
-os.environ.setdefault("OMP_DYNAMIC", "false")
+
+
+def pin_cpu_arm_env(env):
+    env["OMP_NUM_THREADS"] = str(CPU_THREADS)
+    env["OMP_PROC_BIND"] = "close"
+    env["OMP_PLACES"] = "cores"
+    env.setdefault("OMP_DYNAMIC", "false")
+    return env
+
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    pin_cpu_arm_env(os.environ)
 
 import numpy as np  # noqa: E402
 
@@ -75,6 +86,8 @@ def parse():
     ap.add_argument("--layout", default="auto", choices=["auto", "ell", "tile"],
                     help="auto = the library default (ELL layout, factored operator stream); tile = round-1 W/J stream kernels")
     ap.add_argument("--no-readme-mode", action="store_true", help="skip the README-parameter run reported beside the fixed-work line")
+    ap.add_argument("--cpu-arm-only", type=float, default=0.0, metavar="BUDGET_S",
+                    help="(internal) --impl reference: time the CPU arm for the in-process cpu_baseline of the GPU arm and print its measurement")
     return ap.parse_args()
 
 
@@ -257,6 +270,11 @@ def run_reference(args, P, dtype):
     built here (Eigen/gflags absent), so this times the oracle port of its algorithm on the host's physical cores.
     Every timed step runs the full --pcg-iters; if K steps do not fit the time budget, fewer steps are timed."""
     arm = CpuArm(P, args.implicit, dtype)
+    if args.cpu_arm_only > 0:
+        m = arm.measure(args.pcg_iters, 2, 1, budget_s=args.cpu_arm_only)
+        m["threads"] = arm.threads
+        print(json.dumps({"cpu_arm": m}), flush=True)
+        return
     m = arm.measure(args.pcg_iters, args.steps, args.warmup, budget_s=float(os.environ.get("BA_CPU_BUDGET_S", "200")))
     value = m["value"]
     sample = (f"{m['steps_timed']} x [1 LM iteration = 2 linearisations + {m['pcg_per_step']} PCG iterations + trial "
@@ -485,13 +503,20 @@ def run_ours(args, P, dtype):
 
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
-        arm = CpuArm(P, args.implicit, dtype)
-        m = arm.measure(args.pcg_iters, 2, 1, budget_s=float(os.environ.get("BA_CPU_BASELINE_BUDGET_S", "30")))
-        cpu = {"value": m["value"], "unit": "LM it/s", "cores": arm.threads, "kind": "port",
-               "pcg_iters_per_sec": m["pcg"], "steps_timed": m["steps_timed"], "step_seconds": m["step_s"],
-               "sample": f"median of {m['steps_timed']} x [1 LM iteration = 2 linearisations + {m['pcg_per_step']} PCG iterations] "
-                         f"of the same problem after one warm-up step, oracle port (OpenMP, {arm.threads} pinned threads)"}
-        del arm
+        # a child process, so that the OpenMP pinning of the CPU arm never touches this (GPU-driving) process
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--dtype", args.dtype,
+               "--pcg-iters", str(args.pcg_iters), "--cpu-arm-only", os.environ.get("BA_CPU_BASELINE_BUDGET_S", "30")]
+        if args.implicit:
+            cmd.append("--implicit")
+        out = subprocess.run(cmd, capture_output=True, text=True, env=pin_cpu_arm_env(dict(os.environ)))
+        try:
+            m = json.loads([l for l in out.stdout.splitlines() if l.startswith('{"cpu_arm"')][-1])["cpu_arm"]
+            cpu = {"value": m["value"], "unit": "LM it/s", "cores": m["threads"], "kind": "port",
+                   "pcg_iters_per_sec": m["pcg"], "steps_timed": m["steps_timed"], "step_seconds": m["step_s"],
+                   "sample": f"median of {m['steps_timed']} x [1 LM iteration = 2 linearisations + {m['pcg_per_step']} PCG iterations] "
+                             f"of the same problem after one warm-up step, oracle port (OpenMP, {m['threads']} pinned threads), in a child process"}
+        except Exception as exc:
+            cpu = {"value": None, "unit": "LM it/s", "cores": CPU_THREADS, "kind": "port", "error": repr(exc), "stderr": out.stderr[-300:]}
 
     ref_gpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline and dtype == np.float64 and not args.implicit:

@@ -593,6 +593,10 @@ struct ImplT : Impl {
     p2p = okd > 0.5;
     px.ws = opt.world_size;
     px.rank = opt.rank;
+    {
+      const char *e = getenv("BA_XCHG");
+      px.pull = e ? (!strcmp(e, "pull") ? 1 : 0) : 0;
+    }
     return BA_OK;
   }
 

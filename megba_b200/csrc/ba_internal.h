@@ -71,7 +71,9 @@ struct PeerExchange {
   void *data[8];
   unsigned long long *flag[8];
   unsigned long long epoch;
-  int ws, rank, parity, pad;
+  int ws, rank, parity;
+  int pull;   // 0: push (write into the peers' inboxes, poll / read local memory); 1: pull (publish in the own slot and
+              // raise the own flag locally, poll / read the peers' memory) -- same buffer layout, BA_XCHG=push|pull
 };
 
 // device scalar slots (double) read back by the host

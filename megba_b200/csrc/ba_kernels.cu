@@ -821,10 +821,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
         rj[j] = d.r[i];
       }
       p_s[l] = pj[j];
-      if (px.ws > 1) {  // push this rank's partial sums into every rank's inbox (posted stores over NVLink)
+      if (px.ws > 1) {  // push this rank's partial sums into every rank's inbox (posted stores over NVLink);
+                        // pull flavour: into the own slot only
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          if (r < px.ws) {
+          if (r < px.ws && (!px.pull || r == px.rank)) {
             T *slot = reinterpret_cast<T *>(px.data[r]) + ((size_t)(px.parity * px.ws + px.rank) * 2) * rs;
             slot[i] = sb;
             if (INIT) slot[rs + i] = sa;
@@ -845,10 +846,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
     // while someone still reads it.
     __threadfence_system();
     cl.sync();
-    if (rank == 0 && tid < px.ws)
+    if (rank == 0 && tid < px.ws && (!px.pull || tid == px.rank))
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flag[tid] + px.parity * 8 + px.rank), "l"(px.epoch) : "memory");
     if (tid < px.ws) {
-      const unsigned long long *f = px.flag[px.rank] + px.parity * 8 + tid;
+      // push: sender tid's flag in MY memory; pull: sender tid's flag in ITS memory
+      const unsigned long long *f = px.flag[px.pull ? tid : px.rank] + px.parity * 8 + tid;
       unsigned long long v = 0;
       const long long t0 = clock64();
       do {
@@ -868,7 +870,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg_cam_reg(Dev<T> d, const 
         for (int r = 0; r < 8; ++r) {
           pb[r] = pa[r] = T(0);
           if (r < px.ws) {
-            const T *slot = reinterpret_cast<const T *>(px.data[px.rank]) + ((size_t)(px.parity * px.ws + r) * 2) * rs;
+            const T *slot = reinterpret_cast<const T *>(px.data[px.pull ? r : px.rank]) + ((size_t)(px.parity * px.ws + r) * 2) * rs;
             pb[r] = __ldcv(slot + i);
             if (INIT) pa[r] = __ldcv(slot + rs + i);
           }
