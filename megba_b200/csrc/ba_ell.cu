@@ -315,6 +315,13 @@ __host__ __device__ constexpr size_t schur_ell_smem() {
 #ifndef BA_ELL_LATE_HI
 #define BA_ELL_LATE_HI 1
 #endif
+#ifndef BA_ELL_U1
+#define BA_ELL_U1 2
+#endif
+#ifndef BA_ELL_U2
+#define BA_ELL_U2 1
+#endif
+constexpr int ELL_U1 = BA_ELL_U1, ELL_U2 = BA_ELL_U2;  // rows of phase 1 / phase 2 in flight per thread (unroll factors)
 constexpr int ell_min_blocks(int rc) { return (rc == 0 ? 24 : rc <= 2 ? 16 : rc <= 4 ? 12 : 8) / ELL_WARPS > 0 ? (rc == 0 ? 24 : rc <= 2 ? 16 : rc <= 4 ? 12 : 8) / ELL_WARPS : 1; }
 
 template <typename T, int STORE, int MODE, bool INFO, int RC>
@@ -388,7 +395,7 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
     for (int r = 0; r < NC; ++r)
       if (r < wd.D && cc[r] >= 0) first(cs[r], cc[r], ((size_t)wd.row0 + r) * 32 + lane);
   }
-#pragma unroll 2
+#pragma unroll ELL_U1
   for (int r = RC; r < wd.D; ++r) {
     const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
     const int c = __ldg(d.r_cam + slot);
@@ -446,6 +453,7 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
     for (int r = 0; r < NC; ++r)
       if (r < wd.D) second(cs[r], cc[r], ((size_t)wd.row0 + r) * 32 + lane);
   }
+#pragma unroll ELL_U2
   for (int r = RC; r < wd.D; ++r) {
     const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
     const int c = __ldg(d.r_cam + slot);

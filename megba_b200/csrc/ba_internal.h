@@ -46,7 +46,7 @@ constexpr int NREP = 16;        // replicas of the camera-space scatter target (
 constexpr int AUX_GRID = 296;   // 2 CTAs per SM for the small grid-stride kernels
 constexpr int ELL_HEAVY = 32;   // points with more observations than this get a warp of their own
 #ifndef BA_ELL_WARPS
-#define BA_ELL_WARPS 4
+#define BA_ELL_WARPS 2
 #endif
 constexpr int ELL_WARPS = BA_ELL_WARPS;  // warps (slices) per CTA of the ELL kernels
 constexpr int CAMC = 16;        // per-camera constants for the edge kernels: cam[9], c, a, b, a', b', small, pad
