@@ -192,7 +192,11 @@ def make_named(name: str, seed: int = 42) -> BAProblem:
     """`venice-1778` = uniform random graph of that shape (the headline workload since round 1); `venice-1778:bal` = the
     same shape with BAL-like statistics (heavy-tailed tracks, coherent camera windows)."""
     base, _, kind = name.partition(":")
+    base, _, div = base.partition("/")  # "venice-1778/8": one eighth of the points and observations, all cameras (a shard's size)
     nC, nP, nE = BAL_SHAPES[base]
+    if div:
+        nP, nE = nP // int(div), nE // int(div)
+        base = f"{base}/{div}"
     if kind == "bal":
         return make_synthetic(nC, nP, nE, seed=seed, label=f"synthetic-bal:{base}", graph="bal")
     return make_synthetic(nC, nP, nE, seed=seed, label=f"synthetic:{base}")

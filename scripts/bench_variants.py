@@ -7,7 +7,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-CACHE = "/tmp/ba_problem_cache.npz"
+CACHE = "/tmp/ba_problem_cache_%s.npz" % os.environ.get("BA_WORKLOAD", "venice-1778").replace("/", "_").replace(":", "_")
 
 
 def child():
