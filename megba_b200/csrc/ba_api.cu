@@ -442,6 +442,8 @@ struct ImplT : Impl {
   ~ImplT() override {
     if (stream) cudaStreamSynchronize(stream);
     for (auto &e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (d.xpad_tex) cudaDestroyTextureObject(d.xpad_tex);
+    if (d.wj_tex) cudaDestroyTextureObject(d.wj_tex);
     if (arena) cudaFree(arena);
     if (e_info_dev) cudaFree(e_info_dev);
     if (cm_info_dev) cudaFree(cm_info_dev);
@@ -638,16 +640,36 @@ struct ImplT : Impl {
     add(&d.pk_counters, 4); add(&d.pk_partials, 2 * 512); add(&d.pk_timers, 4);
     add(&model_part, std::max<size_t>(g.nW, 1));
     size_t total = 0;
-    for (auto &it : items) total += (it.bytes + 255) / 256 * 256 + 256;
+    for (auto &it : items) total += (it.bytes + 511) / 512 * 512 + 512;
     BA_CUDA(cudaMalloc(&arena, total));
     arena_bytes = total;
     BA_CUDA(cudaMemsetAsync(arena, 0, total, stream));
     size_t off = 0;
     for (auto &it : items) {
       *it.ptr = (char *)arena + off;
-      off += (it.bytes + 255) / 256 * 256 + 256;
+      off += (it.bytes + 511) / 512 * 512 + 512;
     }
     d.gc = d.Hpp + 81 * nC;
+    {
+      // linear texture over xpad (16-byte texels); only read by the BA_ELL_TEX experiment build
+      cudaResourceDesc rd{};
+      rd.resType = cudaResourceTypeLinear;
+      rd.res.linear.devPtr = d.xpad;
+      rd.res.linear.sizeInBytes = sizeof(T) * (size_t)CamPad<T>::N * nC;
+      rd.res.linear.desc = sizeof(T) == 8 ? cudaCreateChannelDesc<int4>() : cudaCreateChannelDesc<float4>();
+      cudaTextureDesc td{};
+      td.readMode = cudaReadModeElementType;
+      d.xpad_tex = 0;
+      if (cudaCreateTextureObject(&d.xpad_tex, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); d.xpad_tex = 0; }
+      d.wj_tex = 0;
+      const size_t wj_bytes = sizeof(T) * (size_t)K * nSlots;
+      if (ell && wj_bytes / (2 * sizeof(T)) < (1ull << 27)) {
+        rd.res.linear.devPtr = d.WJ;
+        rd.res.linear.sizeInBytes = wj_bytes;
+        rd.res.linear.desc = sizeof(T) == 8 ? cudaCreateChannelDesc<int4>() : cudaCreateChannelDesc<float2>();
+        if (cudaCreateTextureObject(&d.wj_tex, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); d.wj_tex = 0; }
+      }
+    }
     d.sB = d.sA + (size_t)NREP * 9 * nC;
     d.nC = (int)nC; d.nPl = (int)nPl; d.nT = g.nT; d.nSlabs = g.nSlabs; d.nChunks = g.nChunks; d.nEl = g.nEl;
     d.implicit = opt.compute_kind == BA_IMPLICIT;

@@ -324,6 +324,49 @@ __host__ __device__ constexpr size_t schur_ell_smem() {
 constexpr int ELL_U1 = BA_ELL_U1, ELL_U2 = BA_ELL_U2;  // rows of phase 1 / phase 2 in flight per thread (unroll factors)
 constexpr int ell_min_blocks(int rc) { return (rc == 0 ? 24 : rc <= 2 ? 16 : rc <= 4 ? 12 : 8) / ELL_WARPS > 0 ? (rc == 0 ? 24 : rc <= 2 ? 16 : rc <= 4 ? 12 : 8) / ELL_WARPS : 1; }
 
+// The gather of the camera vector goes through the TEXTURE path (16-byte texels of xpad): the S*p pass is bound by the
+// LSU data pipe of the SM (86 % busy, profiles/r02_ncu_final_summary.txt), and the texture pipe is a second way into the
+// same L1 -- measured 157.4 us against 166.8 us with LSU gathers.  Moving the stream as well does not pay (phase-2
+// re-read through TEX: 163.8 us, both stream passes: 173.0 us; profiles/r02_edge_variants.txt).  BA_ELL_TEX=0: LSU only.
+#ifndef BA_ELL_TEX
+#define BA_ELL_TEX 1
+#endif
+__device__ __forceinline__ void gather_cam_tex(cudaTextureObject_t tex, int c, double *x) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int4 v = tex1Dfetch<int4>(tex, 5 * c + k);
+    x[2 * k] = __hiloint2double(v.y, v.x);
+    x[2 * k + 1] = __hiloint2double(v.w, v.z);
+  }
+}
+__device__ __forceinline__ void gather_cam_tex(cudaTextureObject_t tex, int c, float *x) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 v = tex1Dfetch<float4>(tex, 3 * c + k);
+    x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+  }
+}
+
+// the factored stream (8 scalars per slot) through the texture path
+__device__ __forceinline__ void load_stream_tex(cudaTextureObject_t tex, size_t row, int lane, double *v) {
+  const int base = (int)(row * 128) + lane;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int4 t = tex1Dfetch<int4>(tex, base + j * 32);
+    v[2 * j] = __hiloint2double(t.y, t.x);
+    v[2 * j + 1] = __hiloint2double(t.w, t.z);
+  }
+}
+__device__ __forceinline__ void load_stream_tex(cudaTextureObject_t tex, size_t row, int lane, float *v) {
+  const int base = (int)(row * 128) + lane;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = tex1Dfetch<float2>(tex, base + j * 32);
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+
 template <typename T, int STORE, int MODE, bool INFO, int RC>
 __global__ void __launch_bounds__(ELL_THREADS, ell_min_blocks(RC))
 k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
@@ -384,7 +427,8 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
   T t0 = T(0), t1 = T(0), t2 = T(0);
   auto first = [&](const T *s, int c, size_t slot) {
     __align__(16) T g[CamPad<T>::N];
-    gather_cam<T, true>(xin, c, g);
+    if (BA_ELL_TEX) gather_cam_tex(d.xpad_tex, c, g);
+    else gather_cam<T, true>(xin, c, g);
     T om[4];
     if (INFO) load_info<T>(d.r_info, slot, om);
     if (STORE == ST_FACT) fact_first<T, INFO>(s, g, X0, X1, X2, om, t0, t1, t2);
@@ -400,7 +444,8 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
     const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
     const int c = __ldg(d.r_cam + slot);
     T s[K];
-    load_stream<T, K>(d.WJ, row, lane, s);
+    if (BA_ELL_TEX >= 3 && STORE == ST_FACT) load_stream_tex(d.wj_tex, row, lane, s);
+    else load_stream<T, K>(d.WJ, row, lane, s);
     if (c >= 0) first(s, c, slot);
   }
   if (BA_ELL_LATE_HI) load_point_blocks();
@@ -458,7 +503,8 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
     const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
     const int c = __ldg(d.r_cam + slot);
     T s[K];
-    load_stream<T, K>(d.WJ, row, lane, s);
+    if (BA_ELL_TEX >= 2 && STORE == ST_FACT) load_stream_tex(d.wj_tex, row, lane, s);
+    else load_stream<T, K>(d.WJ, row, lane, s);
     second(s, c, slot);
   }
 }

@@ -128,6 +128,9 @@ struct Dev {
                                 // sB has two sets used alternately so the idle one can be cleared by the edge pass)
   T *r, *p, *q, *z, *xbk;       // PCG vectors [9nC]
   T *xpad;                      // [nC][CamPad::N] padded copy of the vector the edge kernel gathers
+  cudaTextureObject_t wj_tex;   // the operator stream as a linear texture of Vec2<T> texels (same experiment)
+  cudaTextureObject_t xpad_tex; // the same buffer as a linear texture of 16-byte texels (experiment BA_ELL_TEX: gather
+                                // through the TEX pipe instead of the LSU pipe)
   PcgState *st;
   int *pk_counters;             // [4] slice counters of the persistent PCG kernel
   double *pk_partials;          // [2][#SMs] per-CTA partial dot products of the persistent PCG kernel
