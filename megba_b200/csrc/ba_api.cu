@@ -444,6 +444,8 @@ struct ImplT : Impl {
     for (auto &e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (d.xpad_tex) cudaDestroyTextureObject(d.xpad_tex);
     if (d.wj_tex) cudaDestroyTextureObject(d.wj_tex);
+    if (d.camc_tex) cudaDestroyTextureObject(d.camc_tex);
+    if (d.camc2_tex) cudaDestroyTextureObject(d.camc2_tex);
     if (arena) cudaFree(arena);
     if (e_info_dev) cudaFree(e_info_dev);
     if (cm_info_dev) cudaFree(cm_info_dev);
@@ -661,6 +663,14 @@ struct ImplT : Impl {
       td.readMode = cudaReadModeElementType;
       d.xpad_tex = 0;
       if (cudaCreateTextureObject(&d.xpad_tex, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); d.xpad_tex = 0; }
+      d.camc_tex = d.camc2_tex = 0;
+      if (ell) {
+        rd.res.linear.sizeInBytes = sizeof(T) * (size_t)CAMC * nC;
+        rd.res.linear.devPtr = d.camc;
+        if (cudaCreateTextureObject(&d.camc_tex, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); d.camc_tex = 0; }
+        rd.res.linear.devPtr = d.camc2;
+        if (cudaCreateTextureObject(&d.camc2_tex, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); d.camc2_tex = 0; }
+      }
       d.wj_tex = 0;
       const size_t wj_bytes = sizeof(T) * (size_t)K * nSlots;
       if (ell && wj_bytes / (2 * sizeof(T)) < (1ull << 27)) {

@@ -66,6 +66,34 @@ __device__ __forceinline__ void load_camc_lite(const T *__restrict__ camc, int c
   rc.small = false;  // for a small-angle camera c = a = 1, b = 0 reproduce the first-order branch exactly
 }
 
+// the same through the texture path (the kernels that gather camera constants per observation are LSU-pipe bound too)
+__device__ __forceinline__ void load_camc_lite_tex(cudaTextureObject_t tex, int c, double *cm, RotConst<double> &rc) {
+  double v[12];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int4 t = tex1Dfetch<int4>(tex, 8 * c + k);
+    v[2 * k] = __hiloint2double(t.y, t.x);
+    v[2 * k + 1] = __hiloint2double(t.w, t.z);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cm[k] = v[k];
+  rc.c = v[9]; rc.a = v[10]; rc.b = v[11]; rc.ap = 0.; rc.bp = 0.; rc.small = false;
+}
+__device__ __forceinline__ void load_camc_lite_tex(cudaTextureObject_t tex, int c, float *cm, RotConst<float> &rc) {
+  float v[12];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 t = tex1Dfetch<float4>(tex, 4 * c + k);
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cm[k] = v[k];
+  rc.c = v[9]; rc.a = v[10]; rc.b = v[11]; rc.ap = 0.f; rc.bp = 0.f; rc.small = false;
+}
+#ifndef BA_HP1_TEX
+#define BA_HP1_TEX 1
+#endif
+
 template <typename T>
 __global__ void __launch_bounds__(128) k_cam_consts(Dev<T> d) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,7 +175,10 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
     if (c < 0) continue;
     T cm[9];
     RotConst<T> rc;
-    if (STORE == ST_FACT) load_camc_lite<T>(d.camc, c, cm, rc);  // this flavour only runs without small-angle cameras
+    if (STORE == ST_FACT) {  // this flavour only runs without small-angle cameras
+      if (BA_HP1_TEX && d.camc_tex) load_camc_lite_tex(d.camc_tex, c, cm, rc);
+      else load_camc_lite<T>(d.camc, c, cm, rc);
+    }
     else load_camc<T>(d.camc, c, cm, rc);
     const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
     T r0, r1, Jp[6];
@@ -1356,7 +1387,8 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_cost(Dev<T> d) {
     const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
     T cm[9];
     RotConst<T> rc;
-    load_camc_lite<T>(d.camc2, c, cm, rc);
+    if (BA_HP1_TEX && d.camc2_tex) load_camc_lite_tex(d.camc2_tex, c, cm, rc);
+    else load_camc_lite<T>(d.camc2, c, cm, rc);
     T s0, s1;
     edge_residual<T>(cm, rc, X0, X1, X2, ob.x, ob.y, s0, s1);
     a_cost += (double)(s0 * s0) + (double)(s1 * s1);

@@ -129,6 +129,7 @@ struct Dev {
   T *r, *p, *q, *z, *xbk;       // PCG vectors [9nC]
   T *xpad;                      // [nC][CamPad::N] padded copy of the vector the edge kernel gathers
   cudaTextureObject_t wj_tex;   // the operator stream as a linear texture of Vec2<T> texels (same experiment)
+  cudaTextureObject_t camc_tex, camc2_tex;  // camc / camc2 as linear textures of 16-byte texels
   cudaTextureObject_t xpad_tex; // the same buffer as a linear texture of 16-byte texels (experiment BA_ELL_TEX: gather
                                 // through the TEX pipe instead of the LSU pipe)
   PcgState *st;
