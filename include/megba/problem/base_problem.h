@@ -99,7 +99,6 @@ class BaseProblem {
     // ---- vertex numbering: ascending ID inside each kind
     std::vector<std::pair<int, BaseVertex<T> *>> cams, pts;
     for (auto &kv : vertices) {
-      if (kv.second->fixed) throw std::runtime_error("fixed vertices are not implemented (nor in the reference)");
       if (kv.second->kind() == CAMERA) cams.push_back(kv);
       else if (kv.second->kind() == POINT) pts.push_back(kv);
       else throw std::runtime_error("vertex of unknown kind");
@@ -108,14 +107,20 @@ class BaseProblem {
     std::sort(pts.begin(), pts.end());
     const int64_t nC = (int64_t)cams.size(), nP = (int64_t)pts.size(), nE = (int64_t)edges.size();
     std::vector<T> cam(9 * nC), pt(3 * nP), obs(2 * nE), info(4 * nE);
+    std::vector<uint8_t> camFixed(nC, 0), ptFixed(nP, 0);
+    bool anyFixed = false;
     for (int64_t c = 0; c < nC; ++c) {
       cams[c].second->absolutePosition = (int)c;
+      camFixed[c] = cams[c].second->fixed ? 1 : 0;
+      anyFixed = anyFixed || cams[c].second->fixed;
       const auto &e = cams[c].second->getEstimation();
       if (e.size() != 9) throw std::runtime_error("camera estimation must have 9 entries");
       for (int k = 0; k < 9; ++k) cam[9 * c + k] = e(k);
     }
     for (int64_t p = 0; p < nP; ++p) {
       pts[p].second->absolutePosition = (int)p;
+      ptFixed[p] = pts[p].second->fixed ? 1 : 0;
+      anyFixed = anyFixed || pts[p].second->fixed;
       const auto &e = pts[p].second->getEstimation();
       if (e.size() != 3) throw std::runtime_error("point estimation must have 3 entries");
       for (int k = 0; k < 3; ++k) pt[3 * p + k] = e(k);
@@ -170,6 +175,7 @@ class BaseProblem {
       bool ok = true;
       if (ok && ws > 1 && ba_comm_init(s, uid) != BA_OK) { fail("ba_comm_init"); ok = false; }
       if (ok && !identityInfo && ba_set_information(s, info.data()) != BA_OK) { fail("ba_set_information"); ok = false; }
+      if (ok && anyFixed && ba_set_fixed(s, camFixed.data(), ptFixed.data()) != BA_OK) { fail("ba_set_fixed"); ok = false; }
       if (ok && ba_set_params(s, cam.data(), pt.data()) != BA_OK) { fail("ba_set_params"); ok = false; }
       int32_t nt = 0;
       if (ok && ba_lm_solve(s, &lm, &pcg, rank == 0 ? trace.data() : nullptr, (int32_t)trace.size(), &nt, 1) != BA_OK) {

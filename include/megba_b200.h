@@ -209,6 +209,13 @@ int ba_get_params_device(ba_solver *s, void *cam_dev, void *pt_dev, void *stream
  * 272-274); the tile layout refuses them in implicit mode.                        */
 int ba_set_information(ba_solver *s, const void *info);
 
+/* Fixed vertices (BaseVertex::fixed, include/vertex/base_vertex.h:34 -- declared upstream, never honoured there,
+ * src/edge/base_edge.cpp:27-36).  cam_fixed[nC] / pt_fixed[nP]: non-zero = the vertex keeps its parameters; either
+ * pointer may be NULL (none fixed).  Its Jacobian columns leave the normal equations (identity diagonal block, zero
+ * gradient, no coupling): the PCG iterates are those of the system reduced to the free vertices.  Default layout
+ * only.  Call before ba_linearize.                                                                                 */
+int ba_set_fixed(ba_solver *s, const uint8_t *cam_fixed, const uint8_t *pt_fixed);
+
 /* HP1.  EdgeVector::forward + buildLinearSystem (src/edge/base_edge.cpp:160-163,
  * src/geo/analytical_derivatives.cu:162-322, src/edge/build_linear_system.cu:243-423
  * or build_implicit_linear_system.cu:208-322) + computeResidualNorm

@@ -23,7 +23,7 @@ BUF_HPP, BUF_HLL, BUF_W, BUF_J, BUF_G, BUF_DX = range(6)
 # every symbol include/megba_b200.h declares (tests check the export list against the header)
 SYMBOLS = [
     "ba_abi_version", "ba_partition_points", "ba_create", "ba_destroy", "ba_last_error",
-    "ba_comm_unique_id", "ba_comm_init", "ba_comm_init_local", "ba_set_params", "ba_get_params", "ba_set_information",
+    "ba_comm_unique_id", "ba_comm_init", "ba_comm_init_local", "ba_set_params", "ba_get_params", "ba_set_information", "ba_set_fixed",
     "ba_linearize", "ba_process_diag", "ba_solve", "ba_solve_async", "ba_solve_wait",
     "ba_set_params_device", "ba_get_params_device", "ba_step_norms", "ba_eval_trial",
     "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
@@ -253,6 +253,11 @@ class Solver:
     def set_information(self, info):
         info = None if info is None else self._a(info)
         self._chk(self.L.ba_set_information(self.h, _p(info)), "ba_set_information")
+
+    def set_fixed(self, cam_fixed=None, pt_fixed=None):
+        cf = None if cam_fixed is None else np.ascontiguousarray(cam_fixed, np.uint8)
+        pf = None if pt_fixed is None else np.ascontiguousarray(pt_fixed, np.uint8)
+        self._chk(self.L.ba_set_fixed(self.h, _p(cf), _p(pf)), "ba_set_fixed")
 
     # -- hot path
     def linearize(self) -> float:

@@ -383,6 +383,7 @@ struct Impl {
   virtual int set_params(const void *cam, const void *pt) = 0;
   virtual int get_params(void *cam, void *pt) = 0;
   virtual int set_information(const void *info) = 0;
+  virtual int set_fixed(const unsigned char *cam_fixed, const unsigned char *pt_fixed) = 0;
   virtual int linearize(double *cost) = 0;
   virtual int process_diag(double region, int recover) = 0;
   virtual int solve(const ba_pcg_options *o, int *iters, int *done) = 0;
@@ -414,6 +415,7 @@ struct ImplT : Impl {
   T *e_info_dev = nullptr, *cm_info_dev = nullptr;
   T *pt_full = nullptr;  // [3 nP] gather buffer, world_size > 1 only
   void *coll_scratch = nullptr;  // result buffer of the in-process allreduce (>= 90 nC scalars)
+  unsigned char *cam_fixed_dev = nullptr, *pt_fixed_dev = nullptr;
   double *model_part = nullptr;  // [nW] point partials of the model decrease (left by the back-substitution pass)
   bool model_valid = false;      // scal[S_MODEL_PT / S_MODEL_CAM] describe the step of the last solve
   double last_cost = 0.;         // F of the current linearisation
@@ -450,6 +452,8 @@ struct ImplT : Impl {
     if (e_info_dev) cudaFree(e_info_dev);
     if (cm_info_dev) cudaFree(cm_info_dev);
     if (r_info_dev) cudaFree(r_info_dev);
+    if (cam_fixed_dev) cudaFree(cam_fixed_dev);
+    if (pt_fixed_dev) cudaFree(pt_fixed_dev);
     if (pt_full) cudaFree(pt_full);
     if (coll_scratch) cudaFree(coll_scratch);
     for (auto *q : ipc_opened) if (q) cudaIpcCloseMemHandle(q);
@@ -854,6 +858,33 @@ struct ImplT : Impl {
       else BA_CUDA(cudaMemcpyAsync(pt, d.pt, sizeof(T) * 3 * g.nPl, cudaMemcpyDeviceToDevice, stream));
     }
     return link_out(caller_stream);
+  }
+
+  // BaseVertex::fixed (include/vertex/base_vertex.h): declared upstream, never honoured there.  Semantics here: a fixed
+  // vertex keeps its parameters; its Jacobian columns leave the normal equations (identity diagonal block, zero
+  // gradient, no coupling), so the PCG iterates are those of the system reduced to the free vertices.
+  int set_fixed(const unsigned char *cf, const unsigned char *pf) override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    if (!g.ell) return fail(BA_ERR_STATE, "fixed vertices need the default (ELL) layout");
+    d.cam_fixed = nullptr;
+    d.pt_fixed = nullptr;
+    if (cf) {
+      if (!cam_fixed_dev) BA_CUDA(cudaMalloc(&cam_fixed_dev, std::max<size_t>(g.nC, 1)));
+      BA_CUDA(cudaMemcpyAsync(cam_fixed_dev, cf, g.nC, cudaMemcpyHostToDevice, stream));
+      d.cam_fixed = cam_fixed_dev;
+    }
+    if (pf) {
+      if (!pt_fixed_dev) BA_CUDA(cudaMalloc(&pt_fixed_dev, std::max<size_t>(g.nPl, 1)));
+      std::vector<unsigned char> h(std::max<size_t>(g.nPl, 1), 0);
+      for (int k = 0; k < g.nPl; ++k) h[k] = pf[g.pt_begin + g.perm[k]];
+      BA_CUDA(cudaMemcpyAsync(pt_fixed_dev, h.data(), g.nPl, cudaMemcpyHostToDevice, stream));
+      BA_CUDA(cudaStreamSynchronize(stream));
+      d.pt_fixed = pt_fixed_dev;
+    }
+    BA_CUDA(launch_cam_consts<T>(d, stream));  // T_c of the fixed cameras
+    BA_CUDA(cudaStreamSynchronize(stream));
+    linearized = false;
+    return BA_OK;
   }
 
   int set_information(const void *info_v) override {
@@ -1623,6 +1654,7 @@ int ba_comm_init_local(ba_solver **solvers, int32_t n) {
 int ba_set_params(ba_solver *s, const void *cam, const void *pt) { BA_FWD(set_params(cam, pt)); }
 int ba_get_params(ba_solver *s, void *cam, void *pt) { BA_FWD(get_params(cam, pt)); }
 int ba_set_information(ba_solver *s, const void *info) { BA_FWD(set_information(info)); }
+int ba_set_fixed(ba_solver *s, const uint8_t *cam_fixed, const uint8_t *pt_fixed) { BA_FWD(set_fixed(cam_fixed, pt_fixed)); }
 int ba_linearize(ba_solver *s, double *cost) { BA_FWD(linearize(cost)); }
 int ba_process_diag(ba_solver *s, double region, int recover) { BA_FWD(process_diag(region, recover)); }
 int ba_solve(ba_solver *s, const ba_pcg_options *o, int32_t *iters, int32_t *done) { BA_FWD(solve(o, iters, done)); }

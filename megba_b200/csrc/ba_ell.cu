@@ -110,8 +110,10 @@ __global__ void __launch_bounds__(128) k_cam_consts(Dev<T> d) {
   o[15] = T(0);
   T tr[CAMT];
   camera_transform<T>(cm, rc, tr);
+  // a fixed camera has no columns: T_c = 0 removes it from both halves of the factored operator
+  const bool fixed = d.cam_fixed && d.cam_fixed[c];
 #pragma unroll
-  for (int k = 0; k < CAMT; ++k) d.camT[(size_t)CAMT * c + k] = tr[k];
+  for (int k = 0; k < CAMT; ++k) d.camT[(size_t)CAMT * c + k] = fixed ? T(0) : tr[k];
   if (rc.small) d.scal[S_ANY_SMALL] = 1.;  // the factored stream is not used while any camera is in the Taylor branch
 }
 
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
   const bool pvalid = wd.heavy || lane < wd.np;
   T X0 = T(0), X1 = T(0), X2 = T(0);
   if (pvalid) { X0 = d.pt[3 * (size_t)p]; X1 = d.pt[3 * (size_t)p + 1]; X2 = d.pt[3 * (size_t)p + 2]; }
+  const bool pfixed = pvalid && d.pt_fixed && d.pt_fixed[p];
   T hl[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) hl[k] = T(0);
@@ -185,12 +188,24 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
     if (STORE == ST_FACT) {
       T sv[8];
       edge_point_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, sv, sv[6], sv[7]);
+      if (pfixed) {  // a fixed point has no columns
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sv[k] = T(0);
+      }
       store_stream<T, K>(d.WJ, row, lane, sv);
 #pragma unroll
       for (int k = 0; k < 6; ++k) Jp[k] = sv[k];
     } else {
       T J[24];
       edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+      if (pfixed) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) J[9 + q] = J[21 + q] = T(0);
+      }
+      if (d.cam_fixed && d.cam_fixed[c]) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) J[q] = J[12 + q] = T(0);
+      }
       store_stream<T, K>(d.WJ, row, lane, J);
 #pragma unroll
       for (int q = 0; q < 3; ++q) { Jp[q] = J[9 + q]; Jp[3 + q] = J[21 + q]; }
@@ -221,6 +236,10 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
     for (int k = 0; k < 12; ++k) hl[k] = warp_sum<T>(hl[k]);
   }
   if (pvalid && (!wd.heavy || lane == 0)) {
+    if (pfixed) {  // identity block, zero gradient: dx_l = 0
+#pragma unroll
+      for (int k = 0; k < 9; ++k) hl[k] = (k % 4 == 0) ? T(1) : T(0);
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) d.Hll[9 * (size_t)p + k] = hl[k];
 #pragma unroll
@@ -1270,13 +1289,14 @@ __global__ void __launch_bounds__(96) k_lin_cam_reduce_fact(Dev<T> d) {
       for (int j = 0; j < 3; ++j) w += Hs[9 * (ba + i) + bb + j] * camT_el<T>(Ts, bb + j, b);
       v += camT_el<T>(Ts, ba + i, a) * w;
     }
+    if (d.cam_fixed && d.cam_fixed[c]) v = (k / 9 == k % 9) ? T(1) : T(0);  // fixed camera: identity block
     d.Hpp[81 * (size_t)c + k] = v;
   } else if (k < 90) {
     const int a = k - 81, ba = 3 * (a / 3);
     T v = T(0);
 #pragma unroll
     for (int i = 0; i < 3; ++i) v += camT_el<T>(Ts, ba + i, a) * gs[ba + i];
-    d.gc[9 * (size_t)c + a] = v;
+    d.gc[9 * (size_t)c + a] = v;  // zero for a fixed camera (T_c = 0)
   }
 }
 

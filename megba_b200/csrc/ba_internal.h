@@ -105,6 +105,9 @@ struct Dev {
   T *camc2;                     // [nC][CAMC] the same for the trial cameras cam + dx_c
   T *camT;                      // [nC][CAMT]
   T *HllInvP, *wP, *XP;         // planes [9][nPlPad], [3][nPlPad], [3][nPlPad] (device order)
+  // fixed vertices (BaseVertex::fixed): their columns leave the system, their parameters never change
+  const unsigned char *cam_fixed;  // [nC] or nullptr
+  const unsigned char *pt_fixed;   // [nPl] device order, or nullptr
   // camera-major static graph
   const int4 *chunk;            // {cam, beg, end, 0}
   const int *cam_chunk_ptr;     // [nC+1]

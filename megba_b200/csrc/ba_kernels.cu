@@ -226,12 +226,14 @@ __global__ void __launch_bounds__(64) k_lin_cam_reduce(Dev<T> d, int dispatch) {
   if (k >= NTRI + 9) return;
   T v = T(0);
   for (int ch = d.cam_chunk_ptr[c]; ch < d.cam_chunk_ptr[c + 1]; ++ch) v += d.cm_part[(size_t)ch * (NTRI + 9) + k];
+  const bool fixed = d.cam_fixed && d.cam_fixed[c];
   if (k >= NTRI) {
-    d.gc[9 * (size_t)c + (k - NTRI)] = v;
+    d.gc[9 * (size_t)c + (k - NTRI)] = fixed ? T(0) : v;
   } else {
     int y = 0, rem = k;
     while (rem >= 9 - y) { rem -= 9 - y; ++y; }
     const int i = y + rem;
+    if (fixed) v = y == i ? T(1) : T(0);  // a fixed camera keeps an identity block: its step stays zero
     d.Hpp[81 * (size_t)c + 9 * y + i] = v;
     d.Hpp[81 * (size_t)c + 9 * i + y] = v;
   }

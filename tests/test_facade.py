@@ -163,6 +163,10 @@ int main(int argc, char **argv) {
     problem.appendVertex(nC + n, new MegBA::PointVertex<T>());
     problem.getVertex(nC + n).setEstimation(std::move(x));
   }
+  if (argc > 2) {  // BaseVertex::fixed through the facade
+    problem.getVertex(0).fixed = true;
+    problem.getVertex(nC + 3).fixed = true;
+  }
   for (const auto &o : obs) {
     auto *e = new E<T>;
     e->appendVertex(&problem.getVertex(o.c));
@@ -211,3 +215,11 @@ int main(int argc, char **argv) {
     dx_i, _, _, _ = O.schur_pcg(O.process_diag(Hpp_i, 1e3)[0], O.process_diag(Hll_i, 1e3)[0], W_i, None, g_i,
                                 np.zeros(9 * P.nC + 3 * P.nP), 30, 0.0, 1e300)
     assert np.linalg.norm(dx - dx_i) > 1e-3 * np.linalg.norm(dx)
+
+    # the same program with camera 0 and point 3 fixed (BaseVertex::fixed -> ba_set_fixed): they keep their parameters
+    r = subprocess.run([str(exe), str(path), "fixed"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    xf = np.array([float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("X ")])
+    x0 = P.x()
+    assert np.array_equal(xf[:9], x0[:9]) and np.array_equal(xf[9 * P.nC + 9:9 * P.nC + 12], x0[9 * P.nC + 9:9 * P.nC + 12])
+    assert np.abs(xf[9:18] - x0[9:18]).max() > 0  # the free cameras still move
