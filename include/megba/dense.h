@@ -23,7 +23,10 @@ class Matrix {
   std::vector<T> v_;  // column-major like Eigen's default
 
  public:
-  Matrix() : v_(static_cast<std::size_t>((R == Dynamic ? 0 : R) * (C == Dynamic ? 0 : C)), T(0)) {}
+  Matrix() {  // (no T(0) for an empty matrix: a symbolic JetVector element cannot be created outside forward())
+    const std::size_t n = static_cast<std::size_t>((R == Dynamic ? 0 : R) * (C == Dynamic ? 0 : C));
+    if (n) v_.assign(n, T(0));
+  }
   Matrix(int rows, int cols) { resize(rows, cols); }
   template <int R2, int C2>
   Matrix(const Matrix<T, R2, C2> &o) { *this = o; }  // NOLINT: implicit like Eigen
@@ -37,7 +40,8 @@ class Matrix {
   void resize(int rows, int cols) {
     if ((R != Dynamic && R != rows) || (C != Dynamic && C != cols)) throw std::runtime_error("Matrix: cannot resize fixed dimension");
     r_ = rows; c_ = cols;
-    v_.assign(static_cast<std::size_t>(rows) * cols, T(0));
+    v_.clear();
+    if (rows * cols != 0) v_.assign(static_cast<std::size_t>(rows) * cols, T(0));
   }
   int rows() const { return r_; }
   int cols() const { return c_; }
@@ -49,6 +53,12 @@ class Matrix {
   T &operator()(int i, int j) { return v_[static_cast<std::size_t>(j) * r_ + i]; }
   const T &operator()(int i, int j) const { return v_[static_cast<std::size_t>(j) * r_ + i]; }
   bool operator==(const Matrix &o) const { return r_ == o.r_ && c_ == o.c_ && v_ == o.v_; }
+  // first n entries of a column vector (Eigen's head(n))
+  Matrix<T, Dynamic, 1> head(int n) const {
+    Matrix<T, Dynamic, 1> h(n, 1);
+    for (int i = 0; i < n; ++i) h(i) = (*this)(i);
+    return h;
+  }
   static Matrix Zero() { return Matrix(); }
   static Matrix Identity() {
     Matrix m;
@@ -56,6 +66,56 @@ class Matrix {
     return m;
   }
 };
+// The arithmetic a residual written on JetVector matrices needs (examples/BAL_Double.cpp:24-32 of the reference):
+// matrix * vector, +, -, unary -, vector / scalar, scalar * vector.  Results are dynamically sized; assigning them to a
+// fixed-size Matrix checks the shape.
+template <typename T, int R1, int C1, int R2, int C2>
+Matrix<T, Dynamic, Dynamic> operator*(const Matrix<T, R1, C1> &a, const Matrix<T, R2, C2> &b) {
+  if (a.cols() != b.rows()) throw std::runtime_error("Matrix: inner dimensions differ");
+  Matrix<T, Dynamic, Dynamic> c(a.rows(), b.cols());
+  for (int i = 0; i < a.rows(); ++i)
+    for (int j = 0; j < b.cols(); ++j) {
+      T acc = a(i, 0) * b(0, j);
+      for (int k = 1; k < a.cols(); ++k) acc = acc + a(i, k) * b(k, j);
+      c(i, j) = acc;
+    }
+  return c;
+}
+template <typename T, int R1, int C1, int R2, int C2>
+Matrix<T, Dynamic, Dynamic> operator+(const Matrix<T, R1, C1> &a, const Matrix<T, R2, C2> &b) {
+  if (a.rows() != b.rows() || a.cols() != b.cols()) throw std::runtime_error("Matrix: shapes differ");
+  Matrix<T, Dynamic, Dynamic> c(a.rows(), a.cols());
+  for (int i = 0; i < a.size(); ++i) c(i) = a(i) + b(i);
+  return c;
+}
+template <typename T, int R1, int C1, int R2, int C2>
+Matrix<T, Dynamic, Dynamic> operator-(const Matrix<T, R1, C1> &a, const Matrix<T, R2, C2> &b) {
+  if (a.rows() != b.rows() || a.cols() != b.cols()) throw std::runtime_error("Matrix: shapes differ");
+  Matrix<T, Dynamic, Dynamic> c(a.rows(), a.cols());
+  for (int i = 0; i < a.size(); ++i) c(i) = a(i) - b(i);
+  return c;
+}
+template <typename T, int R1, int C1>
+Matrix<T, Dynamic, Dynamic> operator-(const Matrix<T, R1, C1> &a) {
+  Matrix<T, Dynamic, Dynamic> c(a.rows(), a.cols());
+  for (int i = 0; i < a.size(); ++i) c(i) = -a(i);
+  return c;
+}
+template <typename T, int R1, int C1>
+Matrix<T, Dynamic, Dynamic> operator/(const Matrix<T, R1, C1> &a, const T &s) {
+  Matrix<T, Dynamic, Dynamic> c(a.rows(), a.cols());
+  for (int i = 0; i < a.size(); ++i) c(i) = a(i) / s;
+  return c;
+}
+template <typename T, int R1, int C1>
+Matrix<T, Dynamic, Dynamic> operator*(const T &s, const Matrix<T, R1, C1> &a) {
+  Matrix<T, Dynamic, Dynamic> c(a.rows(), a.cols());
+  for (int i = 0; i < a.size(); ++i) c(i) = s * a(i);
+  return c;
+}
+template <typename T, int R1, int C1>
+Matrix<T, Dynamic, Dynamic> operator*(const Matrix<T, R1, C1> &a, const T &s) { return s * a; }
+
 using Matrix2d = Matrix<double, 2, 2>;
 using Matrix2f = Matrix<float, 2, 2>;
 }  // namespace Dense

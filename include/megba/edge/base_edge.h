@@ -1,51 +1,69 @@
 // megba/edge/base_edge.h -- BaseEdge with the reference's residual plug-in seam
 //   virtual JVD<T> forward() = 0            (include/edge/base_edge.h:43)
-// In the reference forward() builds a JetVector expression that is evaluated for ALL edges at once
-// (EdgeVector::forward, src/edge/base_edge.cpp:160-163).  Here forward() is called once, symbolically:
-// the JVD it returns is a small tag naming the fused CUDA residual (see geo/geo.cuh).  Only the
-// analytical BAL reprojection edge exists on this path; anything else is rejected loudly.
+// In the reference forward() builds a JetVector expression that is evaluated for ALL edges at once, one kernel launch
+// per operator (EdgeVector::forward, src/edge/base_edge.cpp:160-163).  Here forward() is called ONCE, on the host, with
+// symbolic JetVectors (operator/jet_vector.h): either it names the fused analytical BAL residual
+// (geo::AnalyticalDerivativesKernelMatrix -> a tag, evaluated by the hand-written kernels), or its expression tape is
+// compiled to a bytecode that the library evaluates per observation on the GPU with forward-mode automatic
+// differentiation (ba_set_residual_program) -- the user-defined-residual path of the reference's BAL_Double.cpp.
 #pragma once
 #include <stdexcept>
 #include <utility>
 #include <vector>
 
 #include "../common.h"
+#include "../dense.h"
+#include "../operator/jet_vector.h"
 #include "../vertex/base_vertex.h"
 
 namespace MegBA {
 enum EdgeKind { ONE, ONE_CAMERA_ONE_POINT, TWO_CAMERA, MULTI };
 
-// What forward() returns: a handle on the residual program (the reference's JVD<T> is an Eigen matrix of
-// JetVectors that owns device slabs; the fused kernels need neither).
 enum class ResidualProgram { NONE, BAL_ANALYTICAL };
+
+// What forward() works with and returns: a matrix of JetVectors, like the reference's
+// JVD<T> = Eigen::Matrix<JetVector<T>, Dynamic, Dynamic>; `program` is set by the fused-residual entry points of geo.
 template <typename T>
-struct JVD {
+struct JVD : public Dense::Matrix<JetVector<T>, Dense::Dynamic, Dense::Dynamic> {
+  using Base = Dense::Matrix<JetVector<T>, Dense::Dynamic, Dense::Dynamic>;
   ResidualProgram program{ResidualProgram::NONE};
-  int rows{0}, cols{0};
+  JVD() = default;
+  JVD(int r, int c) : Base(r, c) {}
+  template <int R, int C>
+  JVD(const Dense::Matrix<JetVector<T>, R, C> &m) : Base(m) {}  // NOLINT: implicit like Eigen
 };
 
-// View of a vertex's estimation inside forward(): only identity/slicing is meaningful symbolically.
+// A vertex as forward() sees it: its estimation as symbolic inputs.
 template <typename T>
-struct EstimationView {
-  int rows{0};
-  const EstimationView &getEstimation() const { return *this; }
-  const EstimationView *operator&() const { return this; }
-  EstimationView operator()(int, int) const { return *this; }
+struct VertexView {
+  JVD<T> estimation;
+  const JVD<T> &getEstimation() const { return estimation; }
 };
 
 template <typename T>
 class EdgeWrapper {
-  std::vector<EstimationView<T>> views_;
-  EstimationView<T> measurement_;
+  std::vector<VertexView<T>> views_;
+  JVD<T> measurement_;
 
  public:
+  // inputs of the residual program: vertex 0 (camera) = 0..8, vertex 1 (point) = 9..11, measurement = 12..13
   void bind(const std::vector<BaseVertex<T> *> &vs, int measRows) {
     views_.clear();
-    for (auto *v : vs) views_.push_back(EstimationView<T>{v->getEstimation().rows()});
-    measurement_.rows = measRows;
+    int next = 0;
+    for (auto *v : vs) {
+      VertexView<T> vv;
+      const int n = v->getEstimation().rows() * v->getEstimation().cols();
+      vv.estimation = JVD<T>(n, 1);
+      for (int i = 0; i < n; ++i) vv.estimation(i) = JetVector<T>::input(next++);
+      views_.push_back(std::move(vv));
+    }
+    if (next != 12 || measRows != 2)
+      throw std::runtime_error("edges of this path join a 9-parameter camera and a 3-parameter point with a 2-vector measurement");
+    measurement_ = JVD<T>(measRows, 1);
+    for (int i = 0; i < measRows; ++i) measurement_(i) = JetVector<T>::input(next++);
   }
-  const EstimationView<T> &operator[](std::size_t n) const { return views_.at(n); }
-  const EstimationView<T> &getMeasurement() const { return measurement_; }
+  const VertexView<T> &operator[](std::size_t n) const { return views_.at(n); }
+  const JVD<T> &getMeasurement() const { return measurement_; }
 };
 
 template <typename T>
@@ -80,6 +98,6 @@ class BaseEdge {
 
  protected:
   const EdgeWrapper<T> &getVertices() { return _edgeWrapper; }
-  const EstimationView<T> &getMeasurement() const { return _edgeWrapper.getMeasurement(); }
+  const JVD<T> &getMeasurement() const { return _edgeWrapper.getMeasurement(); }
 };
 }  // namespace MegBA

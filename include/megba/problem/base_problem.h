@@ -9,6 +9,8 @@
 //   ba_set_params / ba_lm_solve / ba_get_params         -> H2D, LMAlgo::solveCUDA, writeBack (:250-272)
 #pragma once
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -91,11 +93,36 @@ class BaseProblem {
 
   void solve() {
     if (edges.empty()) throw std::runtime_error("solve(): the graph has no edges");
-    // ---- symbolic forward(): which residual is this edge type?
-    edges[0]->bindSymbolic();
-    const JVD<T> prog = edges[0]->forward();
-    if (prog.program != ResidualProgram::BAL_ANALYTICAL)
-      throw std::runtime_error("solve(): only geo::AnalyticalDerivativesKernelMatrix edges are implemented on this path");
+    // ---- symbolic forward(): the residual of this edge type, either the fused analytical BAL edge (a tag) or a
+    // JetVector expression recorded on a tape and compiled to the bytecode the library differentiates on the GPU
+    prog::Tape tape;
+    prog::Program program;
+    bool userProgram = false;
+    {
+      struct Scope {
+        explicit Scope(prog::Tape *t) { prog::current() = t; }
+        ~Scope() { prog::current() = nullptr; }
+      } scope(&tape);
+      edges[0]->bindSymbolic();
+      const JVD<T> out = edges[0]->forward();
+      if (out.program != ResidualProgram::BAL_ANALYTICAL) {
+        if (out.rows() != 2 || out.cols() != 1) throw std::runtime_error("solve(): forward() must return a 2x1 residual");
+        program = prog::compile(tape, out(0).id(), out(1).id(), BA_PROGRAM_MAX_SLOTS);
+        userProgram = true;
+        if (const char *dump = std::getenv("MEGBA_PROGRAM_DUMP")) {  // the compiled residual, for inspection and tests
+          if (FILE *f = std::fopen(dump, "w")) {
+            std::fprintf(f, "program %d %d %d %d %d\n", program.n_instr(), (int)program.consts.size(), program.n_slots,
+                         program.out[0], program.out[1]);
+            for (int i = 0; i < program.n_instr(); ++i) {
+              const uint8_t *q = &program.code[6 * (size_t)i];
+              std::fprintf(f, "%d %d %d %d %d %d\n", q[0], q[1], q[2], q[3], q[4], q[5]);
+            }
+            for (double k : program.consts) std::fprintf(f, "%.17g\n", k);
+            std::fclose(f);
+          }
+        }
+      }
+    }
     // ---- vertex numbering: ascending ID inside each kind
     std::vector<std::pair<int, BaseVertex<T> *>> cams, pts;
     for (auto &kv : vertices) {
@@ -176,6 +203,9 @@ class BaseProblem {
       if (ok && ws > 1 && ba_comm_init(s, uid) != BA_OK) { fail("ba_comm_init"); ok = false; }
       if (ok && !identityInfo && ba_set_information(s, info.data()) != BA_OK) { fail("ba_set_information"); ok = false; }
       if (ok && anyFixed && ba_set_fixed(s, camFixed.data(), ptFixed.data()) != BA_OK) { fail("ba_set_fixed"); ok = false; }
+      if (ok && userProgram &&
+          ba_set_residual_program(s, program.n_instr(), program.code.data(), (int32_t)program.consts.size(), program.consts.data(),
+                                  program.n_slots, program.out) != BA_OK) { fail("ba_set_residual_program"); ok = false; }
       if (ok && ba_set_params(s, cam.data(), pt.data()) != BA_OK) { fail("ba_set_params"); ok = false; }
       int32_t nt = 0;
       if (ok && ba_lm_solve(s, &lm, &pcg, rank == 0 ? trace.data() : nullptr, (int32_t)trace.size(), &nt, 1) != BA_OK) {

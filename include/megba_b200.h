@@ -216,6 +216,20 @@ int ba_set_information(ba_solver *s, const void *info);
  * only.  Call before ba_linearize.                                                                                 */
 int ba_set_fixed(ba_solver *s, const uint8_t *cam_fixed, const uint8_t *pt_fixed);
 
+/* User-defined residuals: the reference's plug-in seam BaseEdge::forward() on JetVectors (include/edge/base_edge.h:43,
+ * include/operator/jet_vector.h:23-171, one kernel launch per operator).  Here the residual is a register bytecode --
+ * the facade records forward() once on a tape and compiles it (include/megba/operator/jet_vector.h) -- that the library
+ * evaluates per observation with forward-mode automatic differentiation in one fused kernel; the Jacobians go into the
+ * Jacobian operator stream, everything downstream (assembly, Schur PCG, LM) is the path of the built-in residual.
+ *   code[n_instr][6] = {op, dst, a, b, c, d} (register numbers < n_slots <= BA_PROGRAM_MAX_SLOTS);
+ *   ops: 0 INPUT (a = input: 0..8 camera, 9..11 point, 12..13 observation), 1 CONST (a = index into consts),
+ *        2 ADD, 3 SUB, 4 MUL, 5 DIV, 6 NEG, 7 SQRT, 8 SIN, 9 COS, 10 SELGT (a > b ? c : d);
+ *   out_slot[2] = registers holding the two residual components at the end.
+ * n_instr = 0 restores the built-in analytical BAL residual.  Default layout only.                                 */
+#define BA_PROGRAM_MAX_SLOTS 48
+int ba_set_residual_program(ba_solver *s, int32_t n_instr, const uint8_t *code, int32_t n_const, const double *consts,
+                            int32_t n_slots, const int32_t *out_slot);
+
 /* HP1.  EdgeVector::forward + buildLinearSystem (src/edge/base_edge.cpp:160-163,
  * src/geo/analytical_derivatives.cu:162-322, src/edge/build_linear_system.cu:243-423
  * or build_implicit_linear_system.cu:208-322) + computeResidualNorm

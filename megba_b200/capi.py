@@ -24,6 +24,7 @@ BUF_HPP, BUF_HLL, BUF_W, BUF_J, BUF_G, BUF_DX = range(6)
 SYMBOLS = [
     "ba_abi_version", "ba_partition_points", "ba_create", "ba_destroy", "ba_last_error",
     "ba_comm_unique_id", "ba_comm_init", "ba_comm_init_local", "ba_set_params", "ba_get_params", "ba_set_information", "ba_set_fixed",
+    "ba_set_residual_program",
     "ba_linearize", "ba_process_diag", "ba_solve", "ba_solve_async", "ba_solve_wait",
     "ba_set_params_device", "ba_get_params_device", "ba_step_norms", "ba_eval_trial",
     "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
@@ -258,6 +259,17 @@ class Solver:
         cf = None if cam_fixed is None else np.ascontiguousarray(cam_fixed, np.uint8)
         pf = None if pt_fixed is None else np.ascontiguousarray(pt_fixed, np.uint8)
         self._chk(self.L.ba_set_fixed(self.h, _p(cf), _p(pf)), "ba_set_fixed")
+
+    def set_residual_program(self, code=None, consts=(), n_slots=0, out=(0, 0)):
+        """code: [n_instr, 6] uint8 {op, dst, a, b, c, d} (include/megba_b200.h); None restores the analytical model."""
+        if code is None:
+            self._chk(self.L.ba_set_residual_program(self.h, 0, None, 0, None, 0, None), "ba_set_residual_program")
+            return
+        code = np.ascontiguousarray(code, np.uint8).reshape(-1, 6)
+        k = np.ascontiguousarray(consts, np.float64)
+        o = np.ascontiguousarray(out, np.int32)
+        self._chk(self.L.ba_set_residual_program(self.h, int(code.shape[0]), _p(code), int(k.size), _p(k) if k.size else None,
+                                                 int(n_slots), _p(o)), "ba_set_residual_program")
 
     # -- hot path
     def linearize(self) -> float:

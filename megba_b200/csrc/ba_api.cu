@@ -22,6 +22,7 @@
 
 #include "../../include/megba_b200.h"
 #include "ba_internal.h"
+#include "ba_program.cuh"
 
 namespace ba {
 
@@ -384,6 +385,8 @@ struct Impl {
   virtual int get_params(void *cam, void *pt) = 0;
   virtual int set_information(const void *info) = 0;
   virtual int set_fixed(const unsigned char *cam_fixed, const unsigned char *pt_fixed) = 0;
+  virtual int set_residual_program(int n_instr, const uint8_t *code, int n_const, const double *consts, int n_slots,
+                                   const int32_t *out_slot) = 0;
   virtual int linearize(double *cost) = 0;
   virtual int process_diag(double region, int recover) = 0;
   virtual int solve(const ba_pcg_options *o, int *iters, int *done) = 0;
@@ -416,6 +419,9 @@ struct ImplT : Impl {
   T *pt_full = nullptr;  // [3 nP] gather buffer, world_size > 1 only
   void *coll_scratch = nullptr;  // result buffer of the in-process allreduce (>= 90 nC scalars)
   unsigned char *cam_fixed_dev = nullptr, *pt_fixed_dev = nullptr;
+  uint2 *prog_code_dev = nullptr;  // user-defined residual (ba_set_residual_program)
+  T *prog_const_dev = nullptr;
+  int store_before_prog = -1;      // the configured stream to go back to when the program is cleared
   double *model_part = nullptr;  // [nW] point partials of the model decrease (left by the back-substitution pass)
   bool model_valid = false;      // scal[S_MODEL_PT / S_MODEL_CAM] describe the step of the last solve
   double last_cost = 0.;         // F of the current linearisation
@@ -453,6 +459,8 @@ struct ImplT : Impl {
     if (cm_info_dev) cudaFree(cm_info_dev);
     if (r_info_dev) cudaFree(r_info_dev);
     if (cam_fixed_dev) cudaFree(cam_fixed_dev);
+    if (prog_code_dev) cudaFree(prog_code_dev);
+    if (prog_const_dev) cudaFree(prog_const_dev);
     if (pt_fixed_dev) cudaFree(pt_fixed_dev);
     if (pt_full) cudaFree(pt_full);
     if (coll_scratch) cudaFree(coll_scratch);
@@ -883,6 +891,68 @@ struct ImplT : Impl {
     }
     BA_CUDA(launch_cam_consts<T>(d, stream));  // T_c of the fixed cameras
     BA_CUDA(cudaStreamSynchronize(stream));
+    linearized = false;
+    return BA_OK;
+  }
+
+  // The residual of every edge as a register program (see ba_program.cuh for the instruction set).  The program
+  // replaces the analytical BAL model in the linearisation, the trial-cost evaluation and ba_eval_edges; the
+  // operator stream becomes the Jacobian (the factored stream is a property of the BAL projection).
+  int set_residual_program(int n_instr, const uint8_t *code, int n_const, const double *consts, int n_slots,
+                           const int32_t *out_slot) override {
+    BA_CUDA(cudaSetDevice(opt.device));
+    if (!g.ell) return fail(BA_ERR_STATE, "a residual program needs the default (ELL) layout");
+    if (n_instr == 0 || !code) {  // back to the analytical model
+      d.prog_code = nullptr;
+      d.prog_const = nullptr;
+      d.prog_n = 0;
+      if (store_before_prog >= 0) store_cfg = store_before_prog;
+      store_before_prog = -1;
+      d.store = store_cfg;
+      linearized = false;
+      return BA_OK;
+    }
+    if (n_instr < 0 || n_const < 0 || (n_const > 0 && !consts) || !out_slot)
+      return fail(BA_ERR_ARG, "residual program: bad argument");
+    if (n_slots < 1 || n_slots > PROG_SLOTS)
+      return fail(BA_ERR_ARG, "residual program: %d registers, the interpreter has %d", n_slots, PROG_SLOTS);
+    std::vector<char> written((size_t)n_slots, 0);
+    std::vector<uint2> h((size_t)n_instr);
+    for (int i = 0; i < n_instr; ++i) {
+      const uint8_t *q = code + 6 * (size_t)i;
+      const int op = q[0], dst = q[1];
+      if (op > 10) return fail(BA_ERR_ARG, "residual program: instruction %d has unknown op %d", i, op);
+      if (dst >= n_slots) return fail(BA_ERR_ARG, "residual program: instruction %d writes register %d of %d", i, dst, n_slots);
+      const int nsrc = op == 0 || op == 1 ? 0 : op == 10 ? 4 : (op >= 6 && op <= 9) ? 1 : 2;
+      if (op == 0 && q[2] >= PROG_NIN) return fail(BA_ERR_ARG, "residual program: instruction %d reads input %d of %d", i, q[2], PROG_NIN);
+      if (op == 1 && q[2] >= n_const) return fail(BA_ERR_ARG, "residual program: instruction %d reads constant %d of %d", i, q[2], n_const);
+      for (int k = 0; k < nsrc; ++k)
+        if (q[2 + k] >= n_slots || !written[q[2 + k]])
+          return fail(BA_ERR_ARG, "residual program: instruction %d reads register %d before it is written", i, q[2 + k]);
+      written[dst] = 1;
+      h[i].x = (unsigned)op | (unsigned)dst << 8 | (unsigned)q[2] << 16 | (unsigned)q[3] << 24;
+      h[i].y = (unsigned)q[4] | (unsigned)q[5] << 8;
+    }
+    for (int k = 0; k < 2; ++k)
+      if (out_slot[k] < 0 || out_slot[k] >= n_slots || !written[out_slot[k]])
+        return fail(BA_ERR_ARG, "residual program: result %d is register %d, which no instruction writes", k, out_slot[k]);
+    std::vector<T> hc((size_t)std::max(n_const, 1), T(0));
+    for (int k = 0; k < n_const; ++k) hc[k] = (T)consts[k];
+    if (prog_code_dev) { cudaFree(prog_code_dev); prog_code_dev = nullptr; }
+    if (prog_const_dev) { cudaFree(prog_const_dev); prog_const_dev = nullptr; }
+    BA_CUDA(cudaMalloc(&prog_code_dev, sizeof(uint2) * h.size()));
+    BA_CUDA(cudaMalloc(&prog_const_dev, sizeof(T) * hc.size()));
+    BA_CUDA(cudaMemcpyAsync(prog_code_dev, h.data(), sizeof(uint2) * h.size(), cudaMemcpyHostToDevice, stream));
+    BA_CUDA(cudaMemcpyAsync(prog_const_dev, hc.data(), sizeof(T) * hc.size(), cudaMemcpyHostToDevice, stream));
+    BA_CUDA(cudaStreamSynchronize(stream));
+    d.prog_code = prog_code_dev;
+    d.prog_const = prog_const_dev;
+    d.prog_n = n_instr;
+    d.prog_out0 = out_slot[0];
+    d.prog_out1 = out_slot[1];
+    if (store_before_prog < 0) store_before_prog = store_cfg;
+    store_cfg = ST_J;
+    d.store = ST_J;
     linearized = false;
     return BA_OK;
   }
@@ -1655,6 +1725,10 @@ int ba_set_params(ba_solver *s, const void *cam, const void *pt) { BA_FWD(set_pa
 int ba_get_params(ba_solver *s, void *cam, void *pt) { BA_FWD(get_params(cam, pt)); }
 int ba_set_information(ba_solver *s, const void *info) { BA_FWD(set_information(info)); }
 int ba_set_fixed(ba_solver *s, const uint8_t *cam_fixed, const uint8_t *pt_fixed) { BA_FWD(set_fixed(cam_fixed, pt_fixed)); }
+int ba_set_residual_program(ba_solver *s, int32_t n_instr, const uint8_t *code, int32_t n_const, const double *consts,
+                            int32_t n_slots, const int32_t *out_slot) {
+  BA_FWD(set_residual_program(n_instr, code, n_const, consts, n_slots, out_slot));
+}
 int ba_linearize(ba_solver *s, double *cost) { BA_FWD(linearize(cost)); }
 int ba_process_diag(ba_solver *s, double region, int recover) { BA_FWD(process_diag(region, recover)); }
 int ba_solve(ba_solver *s, const ba_pcg_options *o, int32_t *iters, int32_t *done) { BA_FWD(solve(o, iters, done)); }

@@ -22,6 +22,7 @@
 #include "ba_device_utils.cuh"
 #include "ba_geometry.cuh"
 #include "ba_internal.h"
+#include "ba_program.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -153,7 +154,7 @@ __device__ __forceinline__ void load_info(const T *__restrict__ r_info, size_t s
 // HP1, point side.  DISPATCH: 0 run; 1 run unless a camera is in the small-angle branch; 2 run only then
 // (the flag is produced on the device by k_cam_consts just before, so the host launches both flavours of a
 // factored-store solver back to back and exactly one of them does the work).
-template <typename T, int STORE, bool INFO>
+template <typename T, int STORE, bool INFO, bool PROG = false>
 __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch) {
   constexpr int K = STORE == ST_FACT ? 8 : 24;
   if (dispatch) {
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
       for (int k = 0; k < 6; ++k) Jp[k] = sv[k];
     } else {
       T J[24];
-      edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+      if (PROG) prog_edge<T, true>(d, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+      else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
       if (pfixed) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) J[9 + q] = J[21 + q] = T(0);
@@ -1131,7 +1133,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_pcg_persistent(const __grid_c
 
 // --------------------------------------------------------------------------------
 // LM scalars: sum (J dx + r)^2 at x and sum r^2 at x + dx in one pass.
-template <typename T>
+template <typename T, bool PROG>
 __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
   const int lane = threadIdx.x & 31, w = blockIdx.x * ELL_WARPS + (threadIdx.x >> 5);
   if (w >= d.nW) return;
@@ -1155,7 +1157,14 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
     for (int k = 0; k < 9; ++k) dc[k] = d.dxc[9 * (size_t)c + k];
     const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
     T J[24], r0, r1;
-    edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    if (PROG) prog_edge<T, true>(d, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    if (PROG) {  // the model lives on the free columns only (the analytical path's dx is zero on fixed vertices anyway)
+      if (d.cam_fixed && d.cam_fixed[c]) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dc[k] = T(0);
+      }
+    }
     T m0 = T(0), m1 = T(0);  // J dx  (JdxpF, lm_algo.cu:61-79)
 #pragma unroll
     for (int k = 0; k < 9; ++k) { m0 += J[k] * dc[k]; m1 += J[12 + k] * dc[k]; }
@@ -1164,9 +1173,12 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
     a_model += (double)((m0 + r0) * (m0 + r0)) + (double)((m1 + r1) * (m1 + r1));
 #pragma unroll
     for (int k = 0; k < 9; ++k) cm[k] += dc[k];  // updateDeltaXTwoVertices, update.cu:14-41
-    rc = rot_const<T>(cm[0], cm[1], cm[2]);
     T s0, s1;
-    edge_residual<T>(cm, rc, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1);
+    if (PROG) prog_edge<T, false>(d, cm, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1, (T *)nullptr);
+    else {
+      rc = rot_const<T>(cm[0], cm[1], cm[2]);
+      edge_residual<T>(cm, rc, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1);
+    }
     a_cost += (double)(s0 * s0) + (double)(s1 * s1);
   }
   a_cost = warp_sum<double>(a_cost);
@@ -1418,7 +1430,7 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_cost(Dev<T> d) {
 }
 
 // debug / parity: r[slot][2], J[slot][24]
-template <typename T>
+template <typename T, bool PROG>
 __global__ void __launch_bounds__(ELL_THREADS) k_eval_edges_ell(Dev<T> d, T *r_out, T *J_out) {
   const int lane = threadIdx.x & 31, w = blockIdx.x * ELL_WARPS + (threadIdx.x >> 5);
   if (w >= d.nW) return;
@@ -1436,7 +1448,8 @@ __global__ void __launch_bounds__(ELL_THREADS) k_eval_edges_ell(Dev<T> d, T *r_o
     load_camc<T>(d.camc, c, cm, rc);
     const T o0 = d.r_obs[2 * slot], o1 = d.r_obs[2 * slot + 1];
     T J[24], r0, r1;
-    edge_residual_jacobian<T>(cm, rc, X0, X1, X2, o0, o1, r0, r1, J);
+    if (PROG) prog_edge<T, true>(d, cm, X0, X1, X2, o0, o1, r0, r1, J);
+    else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, o0, o1, r0, r1, J);
     r_out[2 * slot] = r0;
     r_out[2 * slot + 1] = r1;
     if (J_out) {
@@ -1504,6 +1517,9 @@ cudaError_t launch_linearize_ell(const Dev<T> &d, cudaStream_t st) {
     if (d.store == ST_FACT) {
       launch_lin_ell_s<T, ST_FACT>(d, 1, st);
       launch_lin_ell_s<T, ST_J>(d, 2, st);
+    } else if (d.prog_code) {  // user-defined residual: the interpreter fills the Jacobian stream
+      if (d.r_info) k_lin_ell<T, ST_J, true, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
+      else k_lin_ell<T, ST_J, false, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
     } else {
       launch_lin_ell_s<T, ST_J>(d, 0, st);
     }
@@ -1696,7 +1712,10 @@ cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st) {
   if (d.store == ST_FACT && ell_hp1_fact()) {  // d.store = the stream in effect; xpad must hold T_c dx_c (host: pad_cam)
     k_cam_consts_trial<T><<<(d.nC + 127) / 128, 128, 0, st>>>(d);
     if (d.nW > 0) k_trial_fact<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
-  } else if (d.nW > 0) k_trial_ell<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+  } else if (d.nW > 0) {
+    if (d.prog_code) k_trial_ell<T, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+    else k_trial_ell<T, false><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+  }
   k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nW, 2, d.scal + S_TRIAL_COST);
   return cudaGetLastError();
 }
@@ -1718,7 +1737,10 @@ cudaError_t launch_trial_cost_ell(const Dev<T> &d, cudaStream_t st) {
 
 template <typename T>
 cudaError_t launch_eval_edges_ell(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st) {
-  if (d.nW > 0) k_eval_edges_ell<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, r_slots, J_slots);
+  if (d.nW > 0) {
+    if (d.prog_code) k_eval_edges_ell<T, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, r_slots, J_slots);
+    else k_eval_edges_ell<T, false><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, r_slots, J_slots);
+  }
   return cudaGetLastError();
 }
 

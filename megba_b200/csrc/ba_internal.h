@@ -108,6 +108,10 @@ struct Dev {
   // fixed vertices (BaseVertex::fixed): their columns leave the system, their parameters never change
   const unsigned char *cam_fixed;  // [nC] or nullptr
   const unsigned char *pt_fixed;   // [nPl] device order, or nullptr
+  // user-defined residual (ba_set_residual_program, ba_program.cuh); nullptr = the analytical BAL model
+  const uint2 *prog_code;
+  const T *prog_const;
+  int prog_n, prog_out0, prog_out1;
   // camera-major static graph
   const int4 *chunk;            // {cam, beg, end, 0}
   const int *cam_chunk_ptr;     // [nC+1]

@@ -32,6 +32,7 @@
 
 #include "ba_geometry.cuh"
 #include "ba_internal.h"
+#include "ba_program.cuh"
 #include "ba_device_utils.cuh"
 
 namespace cg = cooperative_groups;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(TE, 3) k_lin_pm(Dev<T> d) {
 // HP1-B: camera-major accumulation of Hpp (upper triangle) and g_c.  One CTA per
 // (camera, chunk of <= CM_CHUNK edges); residual/Jacobian are recomputed from the
 // L2-resident point array instead of being re-read from HBM.
-template <typename T>
+template <typename T, bool PROG>
 __global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm(Dev<T> d, int dispatch) {
   if (dispatch == 2 && d.scal[S_ANY_SMALL] == 0.) return;  // the factored flavour (ba_ell.cu) did the work
   constexpr int NW = CM_THREADS / 32;
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm(Dev<T> d, int dispatch
     const T X0 = d.pt[3 * (size_t)p], X1 = d.pt[3 * (size_t)p + 1], X2 = d.pt[3 * (size_t)p + 2];
     const typename Vec2<T>::type ob = reinterpret_cast<const typename Vec2<T>::type *>(d.cm_obs)[k];
     T J[24], r0, r1;
-    edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    if (PROG) prog_edge<T, true>(d, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
     T Lb[24];
     const T *L = J;
     if (d.cm_info) {
@@ -1170,7 +1172,10 @@ __global__ void __launch_bounds__(256) k_cam_matvec_sub(Dev<T> d, const T *p, co
 // camera side of the linearisation (layout-independent: it walks the camera-major view)
 template <typename T>
 cudaError_t launch_lin_cm(const Dev<T> &d, cudaStream_t st, int dispatch) {
-  if (d.nChunks > 0) k_lin_cm<T><<<d.nChunks, CM_THREADS, 0, st>>>(d, dispatch);
+  if (d.nChunks > 0) {
+    if (d.prog_code) k_lin_cm<T, true><<<d.nChunks, CM_THREADS, 0, st>>>(d, dispatch);
+    else k_lin_cm<T, false><<<d.nChunks, CM_THREADS, 0, st>>>(d, dispatch);
+  }
   k_lin_cam_reduce<T><<<d.nC, 64, 0, st>>>(d, dispatch);
   return cudaGetLastError();
 }

@@ -1,0 +1,43 @@
+"""User-defined residuals, host side (no GPU): the facade traces the reference's automatic-differentiation BAL edge
+(examples/BAL_Double.cpp of the reference, reproduced in examples/BAL_analytical.inc) into a register program; the
+program -- evaluated here with numpy dual numbers -- must reproduce the oracle's residual and analytical Jacobian,
+including the first-order rotation branch of small-angle cameras."""
+import numpy as np
+
+from megba_b200.synthetic import make_synthetic
+from oracle.oracle import Oracle
+from residual_program import OPS, edge_inputs, eval_program, trace_bal_edge
+from util import rel_fro
+
+
+def test_traced_bal_edge_matches_oracle(tmp_path):
+    prog = trace_bal_edge(tmp_path)
+    code = prog["code"]
+    assert prog["n_slots"] <= 48 and set(code[:, 0]) <= set(range(len(OPS)))
+    assert sorted(code[code[:, 0] == 0][:, 2]) == list(range(14))  # camera 9 + point 3 + measurement 2, each read once
+    assert 10 in code[:, 0]  # the small-angle branch is a per-observation select, not a host-side decision
+    P = make_synthetic(12, 300, 1500, seed=5)
+    P.cam[3, :3] = 0.            # exactly the zero rotation
+    P.cam[7, :3] *= 1e-9         # theta^2 far below the epsilon of the branch
+    O = Oracle(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs)
+    r0, J0 = O.forward(P.cam, P.pt)
+    r, J = eval_program(prog, edge_inputs(P))
+    assert np.isfinite(r).all() and np.isfinite(J).all()
+    assert rel_fro(r, r0) <= 1e-13
+    assert rel_fro(J, J0) <= 1e-11
+    small = np.isin(P.cam_idx, [3, 7])
+    assert small.any() and rel_fro(J[small], J0[small]) <= 1e-9
+
+
+def test_compiler_reuses_registers_and_drops_dead_code(tmp_path):
+    prog = trace_bal_edge(tmp_path)
+    # far fewer registers than instructions: liveness-based reuse; every instruction's result is read later or returned
+    assert prog["n_slots"] < len(prog["code"]) // 2
+    code = prog["code"].astype(int)
+    nsrc = {0: 0, 1: 0, 10: 4, 6: 1, 7: 1, 8: 1, 9: 1}
+    live = set(prog["out"])
+    for op, dst, *src in code[::-1]:
+        assert dst in live, "an instruction whose result nobody reads survived dead-code elimination"
+        live.discard(dst)
+        live.update(src[:nsrc.get(op, 2)])
+    assert not live
