@@ -421,6 +421,8 @@ struct ImplT : Impl {
   unsigned char *cam_fixed_dev = nullptr, *pt_fixed_dev = nullptr;
   uint2 *prog_code_dev = nullptr;  // user-defined residual (ba_set_residual_program)
   T *prog_const_dev = nullptr;
+  int *cm_slot_dev = nullptr;
+  T *r_slots_dev = nullptr;
   int store_before_prog = -1;      // the configured stream to go back to when the program is cleared
   double *model_part = nullptr;  // [nW] point partials of the model decrease (left by the back-substitution pass)
   bool model_valid = false;      // scal[S_MODEL_PT / S_MODEL_CAM] describe the step of the last solve
@@ -461,6 +463,8 @@ struct ImplT : Impl {
     if (cam_fixed_dev) cudaFree(cam_fixed_dev);
     if (prog_code_dev) cudaFree(prog_code_dev);
     if (prog_const_dev) cudaFree(prog_const_dev);
+    if (cm_slot_dev) cudaFree(cm_slot_dev);
+    if (r_slots_dev) cudaFree(r_slots_dev);
     if (pt_fixed_dev) cudaFree(pt_fixed_dev);
     if (pt_full) cudaFree(pt_full);
     if (coll_scratch) cudaFree(coll_scratch);
@@ -942,6 +946,13 @@ struct ImplT : Impl {
     if (prog_const_dev) { cudaFree(prog_const_dev); prog_const_dev = nullptr; }
     BA_CUDA(cudaMalloc(&prog_code_dev, sizeof(uint2) * h.size()));
     BA_CUDA(cudaMalloc(&prog_const_dev, sizeof(T) * hc.size()));
+    if (!cm_slot_dev) {  // the camera side of the linearisation reads the point side's r and J through this map
+      BA_CUDA(cudaMalloc(&cm_slot_dev, sizeof(int) * std::max<size_t>(g.cm_slot.size(), 1)));
+      BA_CUDA(cudaMalloc(&r_slots_dev, sizeof(T) * 2 * std::max<size_t>(g.edge_of_slot.size(), 1)));
+      BA_CUDA(cudaMemcpyAsync(cm_slot_dev, g.cm_slot.data(), sizeof(int) * g.cm_slot.size(), cudaMemcpyHostToDevice, stream));
+      d.cm_slot = cm_slot_dev;
+      d.r_slots = r_slots_dev;
+    }
     BA_CUDA(cudaMemcpyAsync(prog_code_dev, h.data(), sizeof(uint2) * h.size(), cudaMemcpyHostToDevice, stream));
     BA_CUDA(cudaMemcpyAsync(prog_const_dev, hc.data(), sizeof(T) * hc.size(), cudaMemcpyHostToDevice, stream));
     BA_CUDA(cudaStreamSynchronize(stream));

@@ -198,8 +198,12 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
       for (int k = 0; k < 6; ++k) Jp[k] = sv[k];
     } else {
       T J[24];
-      if (PROG) prog_edge<T, true>(d, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
-      else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+      if (PROG) {
+        prog_edge<T, true>(d, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+        typename Vec2<T>::type rv;
+        rv.x = r0; rv.y = r1;
+        reinterpret_cast<typename Vec2<T>::type *>(d.r_slots)[slot] = rv;
+      } else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
       if (pfixed) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) J[9 + q] = J[21 + q] = T(0);
@@ -1157,14 +1161,11 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
     for (int k = 0; k < 9; ++k) dc[k] = d.dxc[9 * (size_t)c + k];
     const typename Vec2<T>::type ob = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_obs) + slot);
     T J[24], r0, r1;
-    if (PROG) prog_edge<T, true>(d, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
-    else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
-    if (PROG) {  // the model lives on the free columns only (the analytical path's dx is zero on fixed vertices anyway)
-      if (d.cam_fixed && d.cam_fixed[c]) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) dc[k] = T(0);
-      }
-    }
+    if (PROG) {  // the interpreter's Jacobian and residual of this linearisation are still in the stream
+      load_stream<T, 24>(d.WJ, (size_t)wd.row0 + r, lane, J);
+      const typename Vec2<T>::type rv = __ldg(reinterpret_cast<const typename Vec2<T>::type *>(d.r_slots) + slot);
+      r0 = rv.x; r1 = rv.y;
+    } else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
     T m0 = T(0), m1 = T(0);  // J dx  (JdxpF, lm_algo.cu:61-79)
 #pragma unroll
     for (int k = 0; k < 9; ++k) { m0 += J[k] * dc[k]; m1 += J[12 + k] * dc[k]; }

@@ -112,6 +112,8 @@ struct Dev {
   const uint2 *prog_code;
   const T *prog_const;
   int prog_n, prog_out0, prog_out1;
+  const int *cm_slot;  // [nEl] slot of each camera-major entry: the camera side reads r and J the point side left
+  T *r_slots;          // [nSlots][2] residuals of the current linearisation
   // camera-major static graph
   const int4 *chunk;            // {cam, beg, end, 0}
   const int *cam_chunk_ptr;     // [nC+1]

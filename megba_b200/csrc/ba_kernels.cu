@@ -32,7 +32,6 @@
 
 #include "ba_geometry.cuh"
 #include "ba_internal.h"
-#include "ba_program.cuh"
 #include "ba_device_utils.cuh"
 
 namespace cg = cooperative_groups;
@@ -182,12 +181,25 @@ __global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm(Dev<T> d, int dispatch
 #pragma unroll
   for (int k = 0; k < NTRI + 9; ++k) acc[k] = T(0);
   for (int k = beg + (int)threadIdx.x; k < end; k += CM_THREADS) {
-    const int p = d.cm_pt[k];
-    const T X0 = d.pt[3 * (size_t)p], X1 = d.pt[3 * (size_t)p + 1], X2 = d.pt[3 * (size_t)p + 2];
-    const typename Vec2<T>::type ob = reinterpret_cast<const typename Vec2<T>::type *>(d.cm_obs)[k];
     T J[24], r0, r1;
-    if (PROG) prog_edge<T, true>(d, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
-    else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    if (PROG) {  // user-defined residual: read what the point-side pass (k_lin_ell) evaluated, from its row-blocked stream
+      using V = typename Vec2<T>::type;
+      const int slot = d.cm_slot[k];
+      const V *src = reinterpret_cast<const V *>(d.WJ) + (size_t)(slot >> 5) * (12 * 32) + (slot & 31);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const V x = __ldg(src + j * 32);
+        J[2 * j] = x.x;
+        J[2 * j + 1] = x.y;
+      }
+      const V rv = __ldg(reinterpret_cast<const V *>(d.r_slots) + slot);
+      r0 = rv.x; r1 = rv.y;
+    } else {
+      const int p = d.cm_pt[k];
+      const T X0 = d.pt[3 * (size_t)p], X1 = d.pt[3 * (size_t)p + 1], X2 = d.pt[3 * (size_t)p + 2];
+      const typename Vec2<T>::type ob = reinterpret_cast<const typename Vec2<T>::type *>(d.cm_obs)[k];
+      edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+    }
     T Lb[24];
     const T *L = J;
     if (d.cm_info) {
