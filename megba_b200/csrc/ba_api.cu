@@ -921,7 +921,9 @@ struct ImplT : Impl {
     if (n_slots < 1 || n_slots > PROG_SLOTS)
       return fail(BA_ERR_ARG, "residual program: %d registers, the interpreter has %d", n_slots, PROG_SLOTS);
     std::vector<char> written((size_t)n_slots, 0);
-    std::vector<uint2> h((size_t)n_instr);
+    std::vector<unsigned> groups((size_t)n_slots, 0);  // derivative groups (3 parameters each) a register can depend on
+    std::vector<uint2> h;
+    h.reserve((size_t)n_instr + 2);
     for (int i = 0; i < n_instr; ++i) {
       const uint8_t *q = code + 6 * (size_t)i;
       const int op = q[0], dst = q[1];
@@ -933,13 +935,29 @@ struct ImplT : Impl {
       for (int k = 0; k < nsrc; ++k)
         if (q[2 + k] >= n_slots || !written[q[2 + k]])
           return fail(BA_ERR_ARG, "residual program: instruction %d reads register %d before it is written", i, q[2 + k]);
+      unsigned ma = 0, mb = 0, md = 0;
+      if (op == 0) md = q[2] < PROG_NDIFF ? 1u << (q[2] / 3) : 0u;
+      else if (op == 10) { ma = groups[q[4]]; mb = groups[q[5]]; md = ma | mb; }
+      else if (nsrc >= 1) { ma = groups[q[2]]; mb = nsrc == 2 ? groups[q[3]] : 0u; md = ma | mb; }
       written[dst] = 1;
-      h[i].x = (unsigned)op | (unsigned)dst << 8 | (unsigned)q[2] << 16 | (unsigned)q[3] << 24;
-      h[i].y = (unsigned)q[4] | (unsigned)q[5] << 8;
+      groups[dst] = md;
+      uint2 w;
+      w.x = (unsigned)op | (unsigned)dst << 8 | (unsigned)q[2] << 16 | (unsigned)q[3] << 24;
+      w.y = (unsigned)q[4] | (unsigned)q[5] << 8 | md << 16 | ma << 20 | mb << 24;
+      h.push_back(w);
     }
     for (int k = 0; k < 2; ++k)
       if (out_slot[k] < 0 || out_slot[k] >= n_slots || !written[out_slot[k]])
         return fail(BA_ERR_ARG, "residual program: result %d is register %d, which no instruction writes", k, out_slot[k]);
+    for (int k = 0; k < 2; ++k) {  // the Jacobian rows are read in full: make the untouched groups of the results zeros
+      const unsigned o = (unsigned)out_slot[k];
+      if (k == 1 && out_slot[1] == out_slot[0]) break;
+      uint2 w;
+      w.x = 11u | o << 8 | o << 16;
+      w.y = 0xfu << 16 | groups[o] << 20;
+      h.push_back(w);
+      groups[o] = 0xf;
+    }
     std::vector<T> hc((size_t)std::max(n_const, 1), T(0));
     for (int k = 0; k < n_const; ++k) hc[k] = (T)consts[k];
     if (prog_code_dev) { cudaFree(prog_code_dev); prog_code_dev = nullptr; }
@@ -958,7 +976,7 @@ struct ImplT : Impl {
     BA_CUDA(cudaStreamSynchronize(stream));
     d.prog_code = prog_code_dev;
     d.prog_const = prog_const_dev;
-    d.prog_n = n_instr;
+    d.prog_n = (int)h.size();
     d.prog_out0 = out_slot[0];
     d.prog_out1 = out_slot[1];
     if (store_before_prog < 0) store_before_prog = store_cfg;

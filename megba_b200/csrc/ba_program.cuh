@@ -11,6 +11,7 @@
 //   0 INPUT  dst = input[a]        a: 0-8 camera, 9-11 point, 12-13 measurement (no derivative)
 //   1 CONST  dst = consts[a]
 //   2 ADD 3 SUB 4 MUL 5 DIV (a, b)   6 NEG 7 SQRT 8 SIN 9 COS (a)   10 SELGT  dst = slot[a] > slot[b] ? slot[c] : slot[d]
+//  11 WIDEN  library-internal (not accepted from callers), see prog_eval
 // dst may be one of the operand registers (the host-side compiler reuses registers by liveness), so every rule
 // below reads its operands' k-th derivative before it writes the result's.
 #pragma once
@@ -26,7 +27,12 @@ __device__ __forceinline__ float prog_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ void prog_sincos(double x, double &s, double &c) { sincos(x, &s, &c); }
 __device__ __forceinline__ void prog_sincos(float x, float &s, float &c) { sincosf(x, &s, &c); }
 
-// in[14] -> res[2] (+ J[2][12] when GRAD)
+// in[14] -> res[2] (+ J[2][12] when GRAD).
+// Derivatives are kept in four groups of three (rotation, translation, intrinsics, point).  The host
+// (ImplT::set_residual_program) propagates which groups each register can depend on and stores, per instruction,
+// the group sets of the result (md) and of the operands (ma, mb) in bits 16-27 of y: a group outside md is neither
+// computed nor stored, an operand group outside ma / mb reads as zero.  The sets are the same for every thread, so
+// the tests on them are uniform branches.  (The rotation half of a BAL residual only ever touches group 0.)
 template <typename T, bool GRAD>
 __device__ __noinline__ void prog_eval(const uint2 *__restrict__ code, const T *__restrict__ consts, int n, int out0, int out1,
                                        const T *in, T *res, T *J) {
@@ -36,69 +42,59 @@ __device__ __noinline__ void prog_eval(const uint2 *__restrict__ code, const T *
   for (int i = 0; i < n; ++i) {
     const uint2 w = __ldg(code + i);
     const int op = w.x & 0xff, dst = (w.x >> 8) & 0xff, a = (w.x >> 16) & 0xff, b = w.x >> 24;
+    const unsigned md = (w.y >> 16) & 0xf, ma = (w.y >> 20) & 0xf, mb = (w.y >> 24) & 0xf;
     T *gd = g + (GRAD ? N * dst : 0);
     const T *ga = g + (GRAD ? N * a : 0), *gb = g + (GRAD ? N * b : 0);
+#define PROG_GROUPS(expr)                                             \
+  if (GRAD) {                                                         \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                   \
+      if (md >> q & 1) {                                              \
+        const bool ha = ma >> q & 1, hb = mb >> q & 1;                \
+        (void)ha; (void)hb;                                           \
+        _Pragma("unroll") for (int k = 3 * q; k < 3 * q + 3; ++k) {   \
+          const T A = ha ? ga[k] : T(0), B = hb ? gb[k] : T(0);       \
+          (void)A; (void)B;                                           \
+          gd[k] = (expr);                                             \
+        }                                                             \
+      }                                                               \
+    }                                                                 \
+  }
     switch (op) {
       case 0: {
+        PROG_GROUPS(k == a ? T(1) : T(0))
         v[dst] = in[a];
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = k == a ? T(1) : T(0);
-        }
       } break;
       case 1: {
         v[dst] = __ldg(consts + a);
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = T(0);
-        }
       } break;
       case 2: {
         const T r = v[a] + v[b];
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = ga[k] + gb[k];
-        }
+        PROG_GROUPS(A + B)
         v[dst] = r;
       } break;
       case 3: {
         const T r = v[a] - v[b];
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = ga[k] - gb[k];
-        }
+        PROG_GROUPS(A - B)
         v[dst] = r;
       } break;
       case 4: {
         const T va = v[a], vb = v[b];
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = va * gb[k] + vb * ga[k];
-        }
+        PROG_GROUPS(va * B + vb * A)
         v[dst] = va * vb;
       } break;
       case 5: {
-        const T ib = T(1) / v[b], q = v[a] * ib;
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = (ga[k] - q * gb[k]) * ib;
-        }
-        v[dst] = q;
+        const T ib = T(1) / v[b], qv = v[a] * ib;
+        PROG_GROUPS((A - qv * B) * ib)
+        v[dst] = qv;
       } break;
       case 6: {
         const T r = -v[a];
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = -ga[k];
-        }
+        PROG_GROUPS(-A)
         v[dst] = r;
       } break;
       case 7: {
         const T s = prog_sqrt(v[a]), h = T(0.5) / s;
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = h * ga[k];
-        }
+        PROG_GROUPS(h * A)
         v[dst] = s;
       } break;
       case 8:
@@ -106,22 +102,32 @@ __device__ __noinline__ void prog_eval(const uint2 *__restrict__ code, const T *
         T s, c;
         prog_sincos(v[a], s, c);
         const T f = op == 8 ? c : -s;
-        if (GRAD) {
-#pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = f * ga[k];
-        }
+        PROG_GROUPS(f * A)
         v[dst] = op == 8 ? s : c;
       } break;
-      default: {  // 10 SELGT
-        const int src = v[a] > v[b] ? (int)(w.y & 0xff) : (int)((w.y >> 8) & 0xff);
+      case 10: {  // SELGT: ma / mb are the group sets of the two candidates
+        const bool first = v[a] > v[b];
+        const int src = first ? (int)(w.y & 0xff) : (int)((w.y >> 8) & 0xff);
         if (GRAD) {
           const T *gs = g + N * src;
+          const unsigned ms = first ? ma : mb;
 #pragma unroll
-          for (int k = 0; k < N; ++k) gd[k] = gs[k];
+          for (int q = 0; q < 4; ++q) {
+            if (md >> q & 1) {
+              const bool hs = ms >> q & 1;
+#pragma unroll
+              for (int k = 3 * q; k < 3 * q + 3; ++k) gd[k] = hs ? gs[k] : T(0);
+            }
+          }
         }
         v[dst] = v[src];
       } break;
+      default: {  // 11 WIDEN (appended by the host for the two results): groups outside ma become explicit zeros
+        PROG_GROUPS(A)
+        v[dst] = v[a];
+      } break;
     }
+#undef PROG_GROUPS
   }
   res[0] = v[out0];
   res[1] = v[out1];
