@@ -31,7 +31,8 @@ def _run(exe, path, *flags, expect_ok=True):
 
 def test_examples_build_and_fail_loudly_without_gpu(tmp_path):
     _build()
-    for exe in ("BAL_Double_analytical", "BAL_Float_analytical", "BAL_Double_analytical_implicit"):
+    for exe in ("BAL_Double_analytical", "BAL_Float_analytical", "BAL_Double_analytical_implicit", "BAL_Double", "BAL_Float",
+                "BAL_Double_implicit"):
         assert os.path.exists(os.path.join(BIN, exe))
     if HAVE_GPU:
         pytest.skip("GPU present: the no-device path cannot be exercised")

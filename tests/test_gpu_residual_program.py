@@ -247,22 +247,26 @@ def test_two_ranks_on_one_device(tmp_path):
     assert np.allclose([t["cost"] for t in out[0]], [t["cost"] for t in tr0], rtol=1e-8)
 
 
-def test_reference_autodiff_example_runs_through_the_facade(tmp_path):
-    """examples/BAL_Double (the reference's automatic-differentiation driver) against the oracle on the same file."""
+@pytest.mark.parametrize("exe,dtype,implicit", [("BAL_Double", np.float64, False), ("BAL_Double_implicit", np.float64, True),
+                                                ("BAL_Float", np.float32, False)])
+def test_reference_autodiff_examples_run_through_the_facade(tmp_path, exe, dtype, implicit):
+    """The reference's three automatic-differentiation drivers (examples/BAL_Double.cpp, BAL_Double_implicit.cpp,
+    BAL_Float.cpp) against the oracle on the same file."""
     build_examples()
     P = make_synthetic(20, 900, 4000, seed=13)
     path = str(tmp_path / "problem-20-900-pre.txt")
     write_bal(path, P)
     flags = ["--max_iter", "4", "--solver_max_iter", "40", "--solver_tol", "1e-6", "--tau", "1e4", "--epsilon1", "1e-3",
              "--epsilon2", "1e-12"]
-    r = subprocess.run([os.path.join(BIN, "BAL_Double"), "--path", path, *flags], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([os.path.join(BIN, exe), "--path", path, *flags], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     m = re.search(r"RESULT iterations (\d+) final_cost (\S+) camera_sum (\S+)", r.stdout)
     assert m, r.stdout
     Q = read_bal(path)
-    O = Oracle(Q.nC, Q.nP, Q.cam_idx, Q.pt_idx, Q.obs)
-    x, k, tr = O.lm_solve(Q.x(), lm_max_iter=4, initial_region=1e4, eps1=1e-3, eps2=1e-12, pcg_max_iter=40, pcg_tol=1e-6,
-                          pcg_refuse=1.0)
+    O = Oracle(Q.nC, Q.nP, Q.cam_idx, Q.pt_idx, Q.obs, dtype)
+    x, k, tr = O.lm_solve(Q.x(), implicit=implicit, lm_max_iter=4, initial_region=1e4, eps1=1e-3, eps2=1e-12, pcg_max_iter=40,
+                          pcg_tol=1e-6, pcg_refuse=1.0)
+    tol = 1e-8 if dtype == np.float64 else 2e-3
     assert int(m.group(1)) == len(tr) - 1
-    assert abs(float(m.group(2)) - tr[-1]["cost"]) <= 1e-8 * tr[-1]["cost"]
-    assert abs(float(m.group(3)) - x[:9 * Q.nC].sum()) <= 1e-7 * abs(x[:9 * Q.nC].sum())
+    assert abs(float(m.group(2)) - tr[-1]["cost"]) <= tol * tr[-1]["cost"]
+    assert abs(float(m.group(3)) - x[:9 * Q.nC].sum()) <= max(tol, 1e-9) * abs(x[:9 * Q.nC].sum()) * 10
