@@ -700,6 +700,17 @@ struct ImplT : Impl {
     d.nC = (int)nC; d.nPl = (int)nPl; d.nT = g.nT; d.nSlabs = g.nSlabs; d.nChunks = g.nChunks; d.nEl = g.nEl;
     d.implicit = opt.compute_kind == BA_IMPLICIT;
     d.ell = ell; d.nW = g.nW; d.nRows = g.nRows; d.nPlPad = (int)nPlPad;
+    d.split = 1;
+    if (ell) {  // few slices (a small problem, or one shard of many): several warps per slice, see k_schur_ell
+      // measured on B200 (profiles/r02_edge_variants.txt): an eighth of Venice (3 884 slices, about one wave of the
+      // 148 x 24 resident warps) 33.6 -> 29.5 us with two warps per slice (31.5 with four); a quarter (7 768 slices)
+      // 49.3 -> 52.1 us; Trafalgar-257 (2 036 slices) 21.3 -> 17.9 -> 17.1 us; Ladybug-49 (243) 16.4 -> 12.9 -> 10.8 us
+      const char *e = getenv("BA_ELL_SPLIT");
+      const int want = e ? atoi(e) : 0;
+      if (want == 1 || want == 2 || want == 4) d.split = want;
+      else if (g.nW < 2500) d.split = 4;
+      else if (g.nW < 4500) d.split = 2;
+    }
     d.wdesc = wdesc; d.cdesc = cdesc; d.nCta = (int)g.cdesc.size(); d.tma_rows = g.tma_rows; d.r_cam = e_cam; d.r_obs = e_obs; d.r_info = nullptr;
     if (ell) {
       // the factored stream needs the register-resident camera kernel (it applies T_c / T_c^T)

@@ -354,9 +354,12 @@ __device__ __forceinline__ void jac_second(const T *J, T u0, T u1, T u2, const T
 }
 
 template <typename T>
-__host__ __device__ constexpr size_t schur_ell_smem() {
-  return (size_t)ELL_WARPS * 32 * 9 * sizeof(T) + (size_t)ELL_WARPS * 32 * sizeof(int);
+__host__ __device__ constexpr size_t schur_ell_smem(int warps = ELL_WARPS) {
+  return (size_t)warps * 32 * 9 * sizeof(T) + (size_t)warps * 32 * sizeof(int);
 }
+// SPLIT warps share one slice (rows r = part, part + SPLIT, ...): used when a shard has too few slices to fill the
+// GPU (k_schur_ell below); the CTA then holds ell_cta_warps(SPLIT) / SPLIT slices
+__host__ __device__ constexpr int ell_cta_warps(int split) { return split > ELL_WARPS ? split : ELL_WARPS; }
 
 // HP2 edge kernel of the ELL layout.  One warp per slice (lane = point) or per heavy point (lane = observation).
 //   phase 1: t_j = sum_e W_e^T x[cam(e)]     thread-local (slice) or one warp sum (heavy point)
@@ -423,16 +426,23 @@ __device__ __forceinline__ void load_stream_tex(cudaTextureObject_t tex, size_t 
   }
 }
 
-template <typename T, int STORE, int MODE, bool INFO, int RC>
-__global__ void __launch_bounds__(ELL_THREADS, ell_min_blocks(RC))
+// SPLIT > 1: a shard with about one wave of slices (an eighth of Venice: 3 900 slices for 3 552 warp slots) is bound by
+// the latency chain of its tallest slices (long-scoreboard stalls, LSU pipe 34 % busy, 31 % of the warp slots active:
+// profiles/r02_ncu_shard8_summary.txt).  SPLIT warps of one CTA then share a slice, each taking every SPLIT-th row;
+// the partial sums t meet in shared memory between the phases (two barriers per pass).
+template <typename T, int STORE, int MODE, bool INFO, int RC, int SPLIT = 1>
+__global__ void __launch_bounds__(ell_cta_warps(SPLIT) * 32, ell_min_blocks(RC) * ELL_WARPS / ell_cta_warps(SPLIT))
 k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check_active) {
+  static_assert(SPLIT == 1 || RC == 0, "register-cached rows and split slices are not combined");
   constexpr int K = STORE == ST_FACT ? 8 : 24;
   constexpr int NC = RC > 0 ? RC : 1;
+  constexpr int NWC = ell_cta_warps(SPLIT), NT = NWC * 32, SPC = NWC / SPLIT;  // warps, threads, slices per CTA
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sv = reinterpret_cast<T *>(smem_raw);
-  int *sc = reinterpret_cast<int *>(sv + ELL_WARPS * 32 * 9);
-  const int tid = threadIdx.x, lane = tid & 31, w = blockIdx.x * ELL_WARPS + (tid >> 5);
+  int *sc = reinterpret_cast<int *>(sv + NWC * 32 * 9);
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, part = wib % SPLIT;
+  const int w = blockIdx.x * SPC + wib / SPLIT;
   const bool wvalid = w < d.nW;
   WDesc wd{0, 0, 0, 0, 0, 0xffff};
   if (wvalid) wd = load_desc(d.wdesc, w);
@@ -475,9 +485,9 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
   }
   if (MODE == SM_FULL && zero_set) {  // clear the replica set the NEXT edge pass will accumulate into
     const unsigned tot = (unsigned)NREP * 9u * (unsigned)d.nC;
-    for (unsigned i = blockIdx.x * ELL_THREADS + tid; i < tot; i += gridDim.x * ELL_THREADS) zero_set[i] = T(0);
+    for (unsigned i = blockIdx.x * NT + tid; i < tot; i += gridDim.x * NT) zero_set[i] = T(0);
   }
-  if (!wvalid) return;  // whole warps only
+  if (SPLIT == 1 && !wvalid) return;  // whole warps only (split: an idle warp has D = 0 and still meets the barriers)
   T *dst = MODE != SM_BACKSUB ? sout + (size_t)(blockIdx.x % NREP) * (9 * (size_t)d.nC) : nullptr;
   // ---- phase 1
   T t0 = T(0), t1 = T(0), t2 = T(0);
@@ -496,7 +506,7 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
       if (r < wd.D && cc[r] >= 0) first(cs[r], cc[r], ((size_t)wd.row0 + r) * 32 + lane);
   }
 #pragma unroll ELL_U1
-  for (int r = RC; r < wd.D; ++r) {
+  for (int r = RC + part; r < wd.D; r += SPLIT) {
     const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
     const int c = __ldg(d.r_cam + slot);
     T s[K];
@@ -506,6 +516,16 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
   }
   if (BA_ELL_LATE_HI) load_point_blocks();
   if (wd.heavy) { t0 = warp_sum<T>(t0); t1 = warp_sum<T>(t1); t2 = warp_sum<T>(t2); }
+  if (SPLIT > 1) {  // the parts' partial sums meet in the (not yet used) scatter staging area
+    T *ex = sv + (size_t)wib * 32 * 9 + 3 * lane;
+    ex[0] = t0; ex[1] = t1; ex[2] = t2;
+    __syncthreads();
+    t0 = t1 = t2 = T(0);
+    const T *all = sv + (size_t)(wib - part) * 32 * 9 + 3 * lane;
+#pragma unroll
+    for (int q = 0; q < SPLIT; ++q) { t0 += all[q * 32 * 9]; t1 += all[q * 32 * 9 + 1]; t2 += all[q * 32 * 9 + 2]; }
+    __syncthreads();
+  }
   // ---- point step
   T u0 = hi[0] * t0 + hi[1] * t1 + hi[2] * t2;
   T u1 = hi[3] * t0 + hi[4] * t1 + hi[5] * t2;
@@ -513,7 +533,7 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
   if (MODE == SM_INIT) { u0 -= wv[0]; u1 -= wv[1]; u2 -= wv[2]; }  // u = Hll^-1 Hlp x0 - w: one pass yields Hpl Hll^-1 Hlp x0 - Hpl w
   if (MODE == SM_BACKSUB) {
     const T l0 = wv[0] - u0, l1 = wv[1] - u1, l2 = wv[2] - u2;
-    const bool owner = pvalid && (!wd.heavy || lane == 0);
+    const bool owner = pvalid && part == 0 && (!wd.heavy || lane == 0);
     if (owner) {
       d.dxl[3 * (size_t)p] = l0;
       d.dxl[3 * (size_t)p + 1] = l1;
@@ -534,7 +554,7 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
             2. * (double)(gv[0] * l0 + gv[1] * l1 + gv[2] * l2);
       }
       m = warp_sum<double>(m);
-      if (lane == 0) d.model_partials[w] = m;
+      if (lane == 0 && part == 0 && wvalid) d.model_partials[w] = m;
     }
     return;
   }
@@ -555,7 +575,7 @@ k_schur_ell(Dev<T> d, const T *__restrict__ xin, T *sout, T *zero_set, int check
       if (r < wd.D) second(cs[r], cc[r], ((size_t)wd.row0 + r) * 32 + lane);
   }
 #pragma unroll ELL_U2
-  for (int r = RC; r < wd.D; ++r) {
+  for (int r = RC + part; r < wd.D; r += SPLIT) {
     const size_t row = (size_t)wd.row0 + r, slot = row * 32 + lane;
     const int c = __ldg(d.r_cam + slot);
     T s[K];
@@ -1549,15 +1569,16 @@ int ell_rc() {
   return v;
 }
 
-template <typename T, int STORE, int MODE, bool INFO, int RC>
+template <typename T, int STORE, int MODE, bool INFO, int RC, int SPLIT = 1>
 static cudaError_t launch_schur_ell_v(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
-  auto kern = k_schur_ell<T, STORE, MODE, INFO, RC>;
-  constexpr size_t smem = schur_ell_smem<T>();
-  const int grid = ell_grid(d.nW);
+  auto kern = k_schur_ell<T, STORE, MODE, INFO, RC, SPLIT>;
+  constexpr int NWC = ell_cta_warps(SPLIT), SPC = NWC / SPLIT;
+  constexpr size_t smem = schur_ell_smem<T>(NWC);
+  const int grid = (d.nW + SPC - 1) / SPC;
   if (check_active && pdl_enabled() && !d.no_pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(ELL_THREADS);
+    cfg.blockDim = dim3(NWC * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1567,12 +1588,14 @@ static cudaError_t launch_schur_ell_v(const Dev<T> &d, const T *xin, T *sout, T 
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, d, xin, sout, zero_set, check_active);
   }
-  kern<<<grid, ELL_THREADS, smem, st>>>(d, xin, sout, zero_set, check_active);
+  kern<<<grid, NWC * 32, smem, st>>>(d, xin, sout, zero_set, check_active);
   return cudaGetLastError();
 }
 
 template <typename T, int STORE, int MODE, bool INFO>
 static cudaError_t launch_schur_ell_rc(const Dev<T> &d, const T *xin, T *sout, T *zero_set, int check_active, cudaStream_t st) {
+  if (d.split == 2) return launch_schur_ell_v<T, STORE, MODE, INFO, 0, 2>(d, xin, sout, zero_set, check_active, st);
+  if (d.split == 4) return launch_schur_ell_v<T, STORE, MODE, INFO, 0, 4>(d, xin, sout, zero_set, check_active, st);
   if constexpr (STORE != ST_FACT) {
     return launch_schur_ell_v<T, STORE, MODE, INFO, 0>(d, xin, sout, zero_set, check_active, st);
   } else if constexpr (INFO || MODE != SM_FULL) {

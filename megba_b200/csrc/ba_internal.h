@@ -112,6 +112,7 @@ struct Dev {
   const uint2 *prog_code;
   const T *prog_const;
   int prog_n, prog_out0, prog_out1;
+  int split;           // warps sharing one slice in the S*p pass (1, 2 or 4; ImplT::init chooses by the shard's size)
   const int *cm_slot;  // [nEl] slot of each camera-major entry: the camera side reads r and J the point side left
   T *r_slots;          // [nSlots][2] residuals of the current linearisation
   // camera-major static graph

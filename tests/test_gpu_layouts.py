@@ -184,3 +184,34 @@ def test_persistent_pcg_kernel(name, dtype):
         assert np.allclose([r["cost"] for r in tra], [r["cost"] for r in trb], rtol=50 * t["cost"])
     else:  # fp32: near convergence the accept / reject decision is within rounding of the summation order
         assert abs(tra[-1]["cost"] - trb[-1]["cost"]) <= 1e-3 * tra[-1]["cost"]
+
+
+@pytest.mark.parametrize("split", ["1", "2", "4"])
+@pytest.mark.parametrize("flavour,name", [("ell-fact", "bal"), ("ell-j", "bal"), ("ell-fact", "small"), ("ell-fact-implicit-kind", "medium")])
+def test_split_slices(monkeypatch, flavour, name, split):
+    """BA_ELL_SPLIT: 1, 2 or 4 warps share one slice of the S*p pass (the library picks 2 for shards of about one wave of
+    slices, 1 otherwise); all three give the step of the oracle, with information matrices too."""
+    monkeypatch.setenv("BA_ELL_SPLIT", split)
+    P = PROBLEMS[name]()
+    rng = np.random.default_rng(11)
+    A = rng.normal(size=(P.nE, 2, 2))
+    info = np.eye(2) + 0.2 * (A + A.transpose(0, 2, 1))
+    t = TOL[np.dtype(np.float64)]
+    for om in (None, info):
+        S = _solver(P, np.float64, flavour)
+        if om is not None:
+            S.set_information(om)
+        S.linearize()
+        S.process_diag(1e3)
+        it, _ = S.solve(max_iter=10, tol=0.0, refuse_ratio=1e300)
+        _, _, dx0, it0 = _oracle_step(P, np.float64, 1e3, 10, info=om)
+        assert it == it0
+        assert rel_fro(S.read(capi.BUF_DX), dx0) <= t["dx"]
+        cnew, msq = S.eval_trial()
+        O = Oracle(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs)
+        x1 = P.x() + dx0
+        r1, _ = O.forward(x1[:9 * P.nC].reshape(-1, 9), x1[9 * P.nC:].reshape(-1, 3), jac=False)
+        c1 = O.cost(r1) if om is None else None
+        if c1 is not None:
+            assert abs(cnew - c1) <= 1e-7 * c1
+        S.close()
