@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -189,6 +191,27 @@ class BaseProblem {
     std::vector<std::string> errors(ws);
     std::vector<ba_lm_trace> trace((size_t)lmo.maxIter + 2);
     int32_t nTrace = 0;
+    // agreement point of the rank threads: returns true when every rank arrived with ok == true
+    std::mutex agreeMutex;
+    std::condition_variable agreeCv;
+    int agreeArrived = 0, agreeGeneration = 0;
+    bool agreeAllOk = true, agreeResult = true;
+    auto agree = [&](bool ok) {
+      if (ws == 1) return ok;
+      std::unique_lock<std::mutex> lock(agreeMutex);
+      agreeAllOk = agreeAllOk && ok;
+      if (++agreeArrived == ws) {
+        agreeResult = agreeAllOk;
+        agreeArrived = 0;
+        agreeAllOk = true;
+        ++agreeGeneration;
+        agreeCv.notify_all();
+        return agreeResult;
+      }
+      const int gen = agreeGeneration;
+      agreeCv.wait(lock, [&] { return agreeGeneration != gen; });
+      return agreeResult;
+    };
     auto worker = [&](int rank) {
       ba_options opt{};
       opt.dtype = std::is_same<T, double>::value ? BA_F64 : BA_F32;
@@ -198,15 +221,19 @@ class BaseProblem {
       opt.world_size = ws;
       ba_solver *s = nullptr;
       auto fail = [&](const char *what) { errors[rank] = std::string(what) + ": " + ba_last_error(s); };
-      if (ba_create(&opt, nC, nP, nE, camIdx.data(), ptIdx.data(), obs.data(), &s) != BA_OK) return fail("ba_create");
-      bool ok = true;
-      if (ok && ws > 1 && ba_comm_init(s, uid) != BA_OK) { fail("ba_comm_init"); ok = false; }
+      bool ok = ba_create(&opt, nC, nP, nE, camIdx.data(), ptIdx.data(), obs.data(), &s) == BA_OK;
+      if (!ok) fail("ba_create");
+      // the ranks agree on success before every step that contains a collective: a rank that failed alone would
+      // otherwise leave the others waiting in ncclCommInitRank / the first allreduce forever
+      if (!agree(ok)) { if (s) ba_destroy(s); return; }
+      if (ws > 1 && ba_comm_init(s, uid) != BA_OK) { fail("ba_comm_init"); ok = false; }
       if (ok && !identityInfo && ba_set_information(s, info.data()) != BA_OK) { fail("ba_set_information"); ok = false; }
       if (ok && anyFixed && ba_set_fixed(s, camFixed.data(), ptFixed.data()) != BA_OK) { fail("ba_set_fixed"); ok = false; }
       if (ok && userProgram &&
           ba_set_residual_program(s, program.n_instr(), program.code.data(), (int32_t)program.consts.size(), program.consts.data(),
                                   program.n_slots, program.out) != BA_OK) { fail("ba_set_residual_program"); ok = false; }
       if (ok && ba_set_params(s, cam.data(), pt.data()) != BA_OK) { fail("ba_set_params"); ok = false; }
+      if (!agree(ok)) { ba_destroy(s); return; }
       int32_t nt = 0;
       if (ok && ba_lm_solve(s, &lm, &pcg, rank == 0 ? trace.data() : nullptr, (int32_t)trace.size(), &nt, 1) != BA_OK) {
         fail("ba_lm_solve");

@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "ba_geometry.cuh"
 #include "ba_internal.h"
@@ -1227,11 +1228,10 @@ static bool *device_flag(bool (&flags)[64]) {
 }
 
 int schur_variant() {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {  // initialised once, thread-safe (the environment does not change under a running solver)
     const char *e = getenv("BA_VAR");
-    v = e ? (atoi(e) & 7) : BA_DEFAULT_VAR;
-  }
+    return e ? (atoi(e) & 7) : BA_DEFAULT_VAR;
+  }();
   return v;
 }
 
@@ -1328,8 +1328,12 @@ static cudaError_t launch_pcg_reg(const Dev<T> &d, T *sB, int cl, int max_iter, 
 
 // 16-CTA clusters are "non-portable": ask the occupancy API once whether this device can host one.
 int pcg_cluster_size() {
-  static int cached = 0;
-  if (cached) return cached;
+  // per device ordinal: the facade drives one host thread per GPU, and the answer is a property of the device
+  static std::atomic<int> cached_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int> &cached = cached_dev[dev & 63];
+  if (cached.load(std::memory_order_relaxed)) return cached.load(std::memory_order_relaxed);
   auto kern = k_pcg_cam_reg<double, 0, 2, false, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
@@ -1347,14 +1351,21 @@ int pcg_cluster_size() {
   int n = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
   if (e != cudaSuccess) cudaGetLastError();
-  cached = (e == cudaSuccess && n >= 1) ? 16 : PCG_CL;
-  return cached;
+  const int v = (e == cudaSuccess && n >= 1) ? 16 : PCG_CL;
+  cached.store(v, std::memory_order_relaxed);
+  return v;
 }
 
 // Cooperative-grid flavour for camera counts that do not fit one cluster at <= 2 rows per thread.
 static int pcg_grid_ctas(int nC) {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  static std::atomic<int> sms_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int sms = sms_dev[dev & 63].load(std::memory_order_relaxed);
+  if (!sms) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms_dev[dev & 63].store(sms, std::memory_order_relaxed);
+  }
   const int want = (9 * nC + 2 * PCG_THREADS - 1) / (2 * PCG_THREADS);
   return want < sms ? want : sms;
 }

@@ -43,6 +43,32 @@ def test_examples_build_and_fail_loudly_without_gpu(tmp_path):
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
 
 
+def _failing_rank(tmp_path):
+    """--world_size 2 where not every rank gets a device (none without a GPU; only rank 0 on a 1-GPU box): the ranks
+    agree on failure before the first collective, solve() throws instead of waiting in ncclCommInitRank."""
+    _build()
+    P = make_synthetic(5, 40, 130, seed=9)
+    path = str(tmp_path / "problem-5-40-pre.txt")
+    write_bal(path, P)
+    r = subprocess.run([os.path.join(BIN, "BAL_Double_analytical"), "--path", path, "--max_iter", "2", "--world_size", "2"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "ba_create" in (r.stdout + r.stderr)
+
+
+def test_ranks_without_devices_fail_together(tmp_path):
+    if HAVE_GPU:
+        pytest.skip("GPU present")
+    _failing_rank(tmp_path)
+
+
+@pytest.mark.gpu
+def test_a_rank_that_fails_alone_does_not_hang_the_others(tmp_path):
+    import torch
+    if torch.cuda.device_count() >= 2:
+        pytest.skip("every rank has a device on this box")
+    _failing_rank(tmp_path)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("exe,dtype,implicit", [("BAL_Double_analytical", np.float64, False),
                                                 ("BAL_Double_analytical_implicit", np.float64, True),
