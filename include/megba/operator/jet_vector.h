@@ -15,7 +15,7 @@
 namespace MegBA {
 namespace prog {
 // keep in sync with megba_b200/csrc/ba_program.cu
-enum Op : uint8_t { INPUT = 0, CONST = 1, ADD = 2, SUB = 3, MUL = 4, DIV = 5, NEG = 6, SQRT = 7, SIN = 8, COS = 9, SELGT = 10 };
+enum Op : uint8_t { INPUT = 0, CONST = 1, ADD = 2, SUB = 3, MUL = 4, DIV = 5, NEG = 6, SQRT = 7, SIN = 8, COS = 9, SELGT = 10, ABS = 11 };
 
 struct Node {
   Op op;
@@ -145,6 +145,7 @@ namespace math {
 template <typename T> JetVector<T> sqrt(const JetVector<T> &a) { return JetVector<T>::node(prog::SQRT, a.id()); }
 template <typename T> JetVector<T> sin(const JetVector<T> &a) { return JetVector<T>::node(prog::SIN, a.id()); }
 template <typename T> JetVector<T> cos(const JetVector<T> &a) { return JetVector<T>::node(prog::COS, a.id()); }
+template <typename T> JetVector<T> abs(const JetVector<T> &a) { return JetVector<T>::node(prog::ABS, a.id()); }
 // a > b ? x : y, evaluated per observation (value and derivatives of the chosen branch)
 template <typename T>
 JetVector<T> select_gt(const JetVector<T> &a, const JetVector<T> &b, const JetVector<T> &x, const JetVector<T> &y) {

@@ -223,9 +223,10 @@ int ba_set_fixed(ba_solver *s, const uint8_t *cam_fixed, const uint8_t *pt_fixed
  * Jacobian operator stream, everything downstream (assembly, Schur PCG, LM) is the path of the built-in residual.
  *   code[n_instr][6] = {op, dst, a, b, c, d} (register numbers < n_slots <= BA_PROGRAM_MAX_SLOTS);
  *   ops: 0 INPUT (a = input: 0..8 camera, 9..11 point, 12..13 observation), 1 CONST (a = index into consts),
- *        2 ADD, 3 SUB, 4 MUL, 5 DIV, 6 NEG, 7 SQRT, 8 SIN, 9 COS, 10 SELGT (a > b ? c : d);
+ *        2 ADD, 3 SUB, 4 MUL, 5 DIV, 6 NEG, 7 SQRT, 8 SIN, 9 COS, 10 SELGT (a > b ? c : d), 11 ABS;
  *   out_slot[2] = registers holding the two residual components at the end.
- * n_instr = 0 restores the built-in analytical BAL residual.  Default layout only.                                 */
+ * Instructions whose value depends on the camera alone are evaluated once per camera, not once per observation
+ * (the library splits the program).  n_instr = 0 restores the built-in analytical BAL residual.  Default layout only. */
 #define BA_PROGRAM_MAX_SLOTS 48
 int ba_set_residual_program(ba_solver *s, int32_t n_instr, const uint8_t *code, int32_t n_const, const double *consts,
                             int32_t n_slots, const int32_t *out_slot);

@@ -23,6 +23,7 @@
 #include "../../include/megba_b200.h"
 #include "ba_internal.h"
 #include "ba_program.cuh"
+#include "ba_program_host.h"
 
 namespace ba {
 
@@ -421,6 +422,7 @@ struct ImplT : Impl {
   unsigned char *cam_fixed_dev = nullptr, *pt_fixed_dev = nullptr;
   uint2 *prog_code_dev = nullptr;  // user-defined residual (ba_set_residual_program)
   T *prog_const_dev = nullptr;
+  T *prog_tab_dev = nullptr;  // frontier tables of the per-camera program (current | trial parameters)
   int *cm_slot_dev = nullptr;
   T *r_slots_dev = nullptr;
   int store_before_prog = -1;      // the configured stream to go back to when the program is cleared
@@ -464,6 +466,7 @@ struct ImplT : Impl {
     if (prog_code_dev) cudaFree(prog_code_dev);
     if (prog_const_dev) cudaFree(prog_const_dev);
     if (cm_slot_dev) cudaFree(cm_slot_dev);
+    if (prog_tab_dev) cudaFree(prog_tab_dev);
     if (r_slots_dev) cudaFree(r_slots_dev);
     if (pt_fixed_dev) cudaFree(pt_fixed_dev);
     if (pt_full) cudaFree(pt_full);
@@ -931,44 +934,15 @@ struct ImplT : Impl {
       return fail(BA_ERR_ARG, "residual program: bad argument");
     if (n_slots < 1 || n_slots > PROG_SLOTS)
       return fail(BA_ERR_ARG, "residual program: %d registers, the interpreter has %d", n_slots, PROG_SLOTS);
-    std::vector<char> written((size_t)n_slots, 0);
-    std::vector<unsigned> groups((size_t)n_slots, 0);  // derivative groups (3 parameters each) a register can depend on
-    std::vector<uint2> h;
-    h.reserve((size_t)n_instr + 2);
-    for (int i = 0; i < n_instr; ++i) {
-      const uint8_t *q = code + 6 * (size_t)i;
-      const int op = q[0], dst = q[1];
-      if (op > 10) return fail(BA_ERR_ARG, "residual program: instruction %d has unknown op %d", i, op);
-      if (dst >= n_slots) return fail(BA_ERR_ARG, "residual program: instruction %d writes register %d of %d", i, dst, n_slots);
-      const int nsrc = op == 0 || op == 1 ? 0 : op == 10 ? 4 : (op >= 6 && op <= 9) ? 1 : 2;
-      if (op == 0 && q[2] >= PROG_NIN) return fail(BA_ERR_ARG, "residual program: instruction %d reads input %d of %d", i, q[2], PROG_NIN);
-      if (op == 1 && q[2] >= n_const) return fail(BA_ERR_ARG, "residual program: instruction %d reads constant %d of %d", i, q[2], n_const);
-      for (int k = 0; k < nsrc; ++k)
-        if (q[2 + k] >= n_slots || !written[q[2 + k]])
-          return fail(BA_ERR_ARG, "residual program: instruction %d reads register %d before it is written", i, q[2 + k]);
-      unsigned ma = 0, mb = 0, md = 0;
-      if (op == 0) md = q[2] < PROG_NDIFF ? 1u << (q[2] / 3) : 0u;
-      else if (op == 10) { ma = groups[q[4]]; mb = groups[q[5]]; md = ma | mb; }
-      else if (nsrc >= 1) { ma = groups[q[2]]; mb = nsrc == 2 ? groups[q[3]] : 0u; md = ma | mb; }
-      written[dst] = 1;
-      groups[dst] = md;
-      uint2 w;
-      w.x = (unsigned)op | (unsigned)dst << 8 | (unsigned)q[2] << 16 | (unsigned)q[3] << 24;
-      w.y = (unsigned)q[4] | (unsigned)q[5] << 8 | md << 16 | ma << 20 | mb << 24;
-      h.push_back(w);
-    }
-    for (int k = 0; k < 2; ++k)
-      if (out_slot[k] < 0 || out_slot[k] >= n_slots || !written[out_slot[k]])
-        return fail(BA_ERR_ARG, "residual program: result %d is register %d, which no instruction writes", k, out_slot[k]);
-    for (int k = 0; k < 2; ++k) {  // the Jacobian rows are read in full: make the untouched groups of the results zeros
-      const unsigned o = (unsigned)out_slot[k];
-      if (k == 1 && out_slot[1] == out_slot[0]) break;
-      uint2 w;
-      w.x = 11u | o << 8 | o << 16;
-      w.y = 0xfu << 16 | groups[o] << 20;
-      h.push_back(w);
-      groups[o] = 0xf;
-    }
+    std::vector<ProgInstr> parsed;
+    int out_def[2];
+    const std::string why = prog_parse(n_instr, code, n_const, n_slots, out_slot, &parsed, out_def);
+    if (!why.empty()) return fail(BA_ERR_ARG, "residual program: %s", why.c_str());
+    static const bool hoist_env = !(getenv("BA_PROG_HOIST") && atoi(getenv("BA_PROG_HOIST")) == 0);
+    const ProgDevice P = prog_lower(parsed, out_def, out_slot, hoist_env);
+    std::vector<uint2> h = P.obs_code;
+    const size_t n_obs_code = h.size();
+    h.insert(h.end(), P.cam_code.begin(), P.cam_code.end());  // one allocation: [per observation | per camera]
     std::vector<T> hc((size_t)std::max(n_const, 1), T(0));
     for (int k = 0; k < n_const; ++k) hc[k] = (T)consts[k];
     if (prog_code_dev) { cudaFree(prog_code_dev); prog_code_dev = nullptr; }
@@ -987,7 +961,14 @@ struct ImplT : Impl {
     BA_CUDA(cudaStreamSynchronize(stream));
     d.prog_code = prog_code_dev;
     d.prog_const = prog_const_dev;
-    d.prog_n = (int)h.size();
+    d.prog_n = (int)n_obs_code;
+    d.prog_cam_code = prog_code_dev + n_obs_code;
+    d.prog_cam_n = (int)P.cam_code.size();
+    d.prog_nf = P.n_frontier;
+    if (prog_tab_dev) { cudaFree(prog_tab_dev); prog_tab_dev = nullptr; }
+    BA_CUDA(cudaMalloc(&prog_tab_dev, sizeof(T) * 2 * std::max<size_t>((size_t)g.nC * PROG_FSTRIDE * P.n_frontier, 1)));
+    d.prog_tab = prog_tab_dev;
+    d.prog_tab2 = prog_tab_dev + (size_t)g.nC * PROG_FSTRIDE * P.n_frontier;
     d.prog_out0 = out_slot[0];
     d.prog_out1 = out_slot[1];
     if (store_before_prog < 0) store_before_prog = store_cfg;

@@ -151,6 +151,28 @@ __device__ __forceinline__ void load_info(const T *__restrict__ r_info, size_t s
 }
 
 // --------------------------------------------------------------------------------
+// User-defined residuals: the camera-only part of the program, once per camera (ba_program_host.h).  trial: at
+// cam + dx_c, values only (the trial cost needs no derivatives).
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(64) k_prog_cam(Dev<T> d, int trial) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.nC) return;
+  T in[PROG_NIN];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) in[k] = d.cam[9 * (size_t)c + k] + (trial ? d.dxc[9 * (size_t)c + k] : T(0));
+#pragma unroll
+  for (int k = 9; k < PROG_NIN; ++k) in[k] = T(0);
+  T *tab = (trial ? d.prog_tab2 : d.prog_tab) + (size_t)c * (PROG_FSTRIDE * d.prog_nf);
+  prog_eval<T, GRAD>(d.prog_cam_code, d.prog_const, d.prog_cam_n, 0, 0, in, (T *)nullptr, (T *)nullptr, (const T *)nullptr, tab);
+}
+template <typename T>
+static void launch_prog_cam(const Dev<T> &d, int trial, cudaStream_t st) {
+  if (!d.prog_code || d.prog_cam_n == 0 || d.nC == 0) return;
+  if (trial) k_prog_cam<T, false><<<(d.nC + 63) / 64, 64, 0, st>>>(d, 1);
+  else k_prog_cam<T, true><<<(d.nC + 63) / 64, 64, 0, st>>>(d, 0);
+}
+
+// --------------------------------------------------------------------------------
 // HP1, point side.  DISPATCH: 0 run; 1 run unless a camera is in the small-angle branch; 2 run only then
 // (the flag is produced on the device by k_cam_consts just before, so the host launches both flavours of a
 // factored-store solver back to back and exactly one of them does the work).
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
     } else {
       T J[24];
       if (PROG) {
-        prog_edge<T, true>(d, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+        prog_edge<T, true>(d, c, d.prog_tab, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
         typename Vec2<T>::type rv;
         rv.x = r0; rv.y = r1;
         reinterpret_cast<typename Vec2<T>::type *>(d.r_slots)[slot] = rv;
@@ -1195,7 +1217,7 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) cm[k] += dc[k];  // updateDeltaXTwoVertices, update.cu:14-41
     T s0, s1;
-    if (PROG) prog_edge<T, false>(d, cm, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1, (T *)nullptr);
+    if (PROG) prog_edge<T, false>(d, c, d.prog_tab2, cm, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1, (T *)nullptr);
     else {
       rc = rot_const<T>(cm[0], cm[1], cm[2]);
       edge_residual<T>(cm, rc, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1);
@@ -1469,7 +1491,7 @@ __global__ void __launch_bounds__(ELL_THREADS) k_eval_edges_ell(Dev<T> d, T *r_o
     load_camc<T>(d.camc, c, cm, rc);
     const T o0 = d.r_obs[2 * slot], o1 = d.r_obs[2 * slot + 1];
     T J[24], r0, r1;
-    if (PROG) prog_edge<T, true>(d, cm, X0, X1, X2, o0, o1, r0, r1, J);
+    if (PROG) prog_edge<T, true>(d, c, d.prog_tab, cm, X0, X1, X2, o0, o1, r0, r1, J);
     else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, o0, o1, r0, r1, J);
     r_out[2 * slot] = r0;
     r_out[2 * slot + 1] = r1;
@@ -1539,6 +1561,7 @@ cudaError_t launch_linearize_ell(const Dev<T> &d, cudaStream_t st) {
       launch_lin_ell_s<T, ST_FACT>(d, 1, st);
       launch_lin_ell_s<T, ST_J>(d, 2, st);
     } else if (d.prog_code) {  // user-defined residual: the interpreter fills the Jacobian stream
+      launch_prog_cam<T>(d, 0, st);
       if (d.r_info) k_lin_ell<T, ST_J, true, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
       else k_lin_ell<T, ST_J, false, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
     } else {
@@ -1737,7 +1760,10 @@ cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st) {
     k_cam_consts_trial<T><<<(d.nC + 127) / 128, 128, 0, st>>>(d);
     if (d.nW > 0) k_trial_fact<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
   } else if (d.nW > 0) {
-    if (d.prog_code) k_trial_ell<T, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+    if (d.prog_code) {
+      launch_prog_cam<T>(d, 1, st);
+      k_trial_ell<T, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
+    }
     else k_trial_ell<T, false><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
   }
   k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nW, 2, d.scal + S_TRIAL_COST);
@@ -1762,7 +1788,10 @@ cudaError_t launch_trial_cost_ell(const Dev<T> &d, cudaStream_t st) {
 template <typename T>
 cudaError_t launch_eval_edges_ell(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st) {
   if (d.nW > 0) {
-    if (d.prog_code) k_eval_edges_ell<T, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, r_slots, J_slots);
+    if (d.prog_code) {
+      launch_prog_cam<T>(d, 0, st);
+      k_eval_edges_ell<T, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, r_slots, J_slots);
+    }
     else k_eval_edges_ell<T, false><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, r_slots, J_slots);
   }
   return cudaGetLastError();

@@ -112,6 +112,9 @@ struct Dev {
   const uint2 *prog_code;
   const T *prog_const;
   int prog_n, prog_out0, prog_out1;
+  const uint2 *prog_cam_code;  // camera-only part, run once per camera (k_prog_cam); fills prog_tab
+  int prog_cam_n, prog_nf;     // its length; frontier values per camera
+  T *prog_tab, *prog_tab2;     // [nC][prog_nf][10] at the current / at the trial parameters
   int split;           // warps sharing one slice in the S*p pass (1, 2 or 4; ImplT::init chooses by the shard's size)
   const int *cm_slot;  // [nEl] slot of each camera-major entry: the camera side reads r and J the point side left
   T *r_slots;          // [nSlots][2] residuals of the current linearisation

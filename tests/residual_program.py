@@ -10,7 +10,7 @@ from conftest import ROOT
 from megba_b200.synthetic import make_synthetic, write_bal
 
 BIN = os.path.join(ROOT, "build", "examples")
-OPS = ("INPUT", "CONST", "ADD", "SUB", "MUL", "DIV", "NEG", "SQRT", "SIN", "COS", "SELGT")
+OPS = ("INPUT", "CONST", "ADD", "SUB", "MUL", "DIV", "NEG", "SQRT", "SIN", "COS", "SELGT", "ABS")
 
 
 def build_examples():
@@ -78,6 +78,9 @@ def eval_program(prog, inputs):
             elif op == 10:
                 m = v[a] > v[b]
                 val, grad = np.where(m, v[c], v[d]), np.where(m, g[c], g[d])
+            elif op == 11:
+                sg = np.where(v[a] > 0, 1., -1.)
+                val, grad = sg * v[a], sg * g[a]
             else:
                 raise ValueError(op)
             v[dst], g[dst] = val, grad

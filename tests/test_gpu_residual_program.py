@@ -124,8 +124,9 @@ class _Asm:
     def sqrt(self, a): return self._emit(7, a)
     def sin(self, a): return self._emit(8, a)
     def cos(self, a): return self._emit(9, a)
+    def abs(self, a): return self._emit(11, a)
     def prog(self, o0, o1):
-        nsrc = {0: 0, 1: 0, 6: 1, 7: 1, 8: 1, 9: 1, 10: 4}
+        nsrc = {0: 0, 1: 0, 6: 1, 7: 1, 8: 1, 9: 1, 10: 4, 11: 1}
         last = {o0: len(self.code), o1: len(self.code)}
         for i, (op, dst, *src) in enumerate(self.code):
             for v in src[:nsrc.get(op, 2)]:
@@ -160,7 +161,7 @@ def _pinhole_euler_program():
     x3 = A.add(A.mul(cy, x1), A.mul(sy, z2))
     z3 = A.sub(A.mul(cy, z2), A.mul(sy, x1))
     px, py, pz = A.add(x3, A.inp(3)), A.add(y2, A.inp(4)), A.add(z3, A.inp(5))
-    depth = A.sqrt(A.add(A.mul(pz, pz), A.const(1e-6)))
+    depth = A.add(A.sqrt(A.add(A.mul(pz, pz), A.const(1e-6))), A.mul(A.const(1e-9), A.abs(pz)))
     f = A.inp(6)
     r0 = A.sub(A.sub(A.inp(7), A.div(A.mul(f, px), depth)), A.inp(12))
     r1 = A.sub(A.sub(A.inp(8), A.div(A.mul(f, py), depth)), A.inp(13))
@@ -198,7 +199,7 @@ def test_rejects_malformed_programs(tmp_path):
     P = make_synthetic(5, 60, 200, seed=45)
     S = _solver(P)
     good = _pinhole_euler_program()
-    bad_op = good["code"].copy(); bad_op[3, 0] = 11
+    bad_op = good["code"].copy(); bad_op[3, 0] = 12
     early = good["code"].copy(); early[0] = [2, 0, 5, 6, 0, 0]  # ADD of registers nothing wrote yet
     for code, consts, n_slots, out, what in (
             (bad_op, good["consts"], good["n_slots"], good["out"], "unknown op"),

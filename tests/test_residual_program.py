@@ -34,7 +34,7 @@ def test_compiler_reuses_registers_and_drops_dead_code(tmp_path):
     # far fewer registers than instructions: liveness-based reuse; every instruction's result is read later or returned
     assert prog["n_slots"] < len(prog["code"]) // 2
     code = prog["code"].astype(int)
-    nsrc = {0: 0, 1: 0, 10: 4, 6: 1, 7: 1, 8: 1, 9: 1}
+    nsrc = {0: 0, 1: 0, 10: 4, 6: 1, 7: 1, 8: 1, 9: 1, 11: 1}
     live = set(prog["out"])
     for op, dst, *src in code[::-1]:
         assert dst in live, "an instruction whose result nobody reads survived dead-code elimination"
