@@ -24,6 +24,7 @@ import os
 import statistics
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -100,15 +101,48 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed regions.  NVML in a thread of this process
+    (the library nvidia-smi itself reads; a sample every 5 ms, so that even the 30 ms timed region of an 8-GPU run gets
+    several), `nvidia-smi -lms 25` in a subprocess when the NVML binding is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReasons bits (nvml.h)
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
+        self.thread = None
+        self.samples = []   # (sm_mhz, reasons_bitmask)
+        self.max_mhz = None
+        self.running = False
+
+    def _nvml_loop(self, nv, h):
+        while self.running:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), int(why)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.running = True
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -117,6 +151,15 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread:
+            self.running = False
+            self.thread.join(timeout=2)
+            sm = [x[0] for x in self.samples]
+            mask = 0
+            for _, w in self.samples:
+                mask |= w
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": sorted(n for n, b in self.BITS.items() if mask & b), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -140,7 +183,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 class CpuArm:
