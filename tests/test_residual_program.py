@@ -1,5 +1,5 @@
 """User-defined residuals, host side (no GPU): the facade traces the reference's automatic-differentiation BAL edge
-(examples/BAL_Double.cpp of the reference, reproduced in examples/BAL_analytical.inc) into a register program; the
+(examples/BAL_Double.cpp of the reference, reproduced in examples/bal_edges.h) into a register program; the
 program -- evaluated here with numpy dual numbers -- must reproduce the oracle's residual and analytical Jacobian,
 including the first-order rotation branch of small-angle cameras."""
 import numpy as np
