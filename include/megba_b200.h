@@ -231,6 +231,18 @@ int ba_set_fixed(ba_solver *s, const uint8_t *cam_fixed, const uint8_t *pt_fixed
 int ba_set_residual_program(ba_solver *s, int32_t n_instr, const uint8_t *code, int32_t n_const, const double *consts,
                             int32_t n_slots, const int32_t *out_slot);
 
+/* How the residual of this handle is evaluated: 0 the built-in analytical BAL kernels, 1 the device interpreter,
+ * 2 a kernel generated from the program and compiled with NVRTC for this GPU when ba_set_residual_program was called
+ * (the default when NVRTC is usable; BA_PROG_JIT=0 in the environment selects the interpreter).                       */
+int ba_residual_program_mode(ba_solver *s);
+
+/* Host-only (no GPU needed): the CUDA source ba_set_residual_program generates for this program, written to src (at most
+ * src_cap bytes incl. the terminator; *src_len = full length), compiled with NVRTC for sm_100a when cubin_bytes is not
+ * NULL (*cubin_bytes = size of the image; the compiler log goes to ba_last_error(NULL) on failure).  dtype: BA_F64/BA_F32. */
+int ba_residual_program_source(int32_t n_instr, const uint8_t *code, int32_t n_const, const double *consts, int32_t n_slots,
+                               const int32_t *out_slot, int32_t dtype, char *src, int64_t src_cap, int64_t *src_len,
+                               int64_t *cubin_bytes);
+
 /* HP1.  EdgeVector::forward + buildLinearSystem (src/edge/base_edge.cpp:160-163,
  * src/geo/analytical_derivatives.cu:162-322, src/edge/build_linear_system.cu:243-423
  * or build_implicit_linear_system.cu:208-322) + computeResidualNorm

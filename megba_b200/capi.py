@@ -24,7 +24,7 @@ BUF_HPP, BUF_HLL, BUF_W, BUF_J, BUF_G, BUF_DX = range(6)
 SYMBOLS = [
     "ba_abi_version", "ba_partition_points", "ba_create", "ba_destroy", "ba_last_error",
     "ba_comm_unique_id", "ba_comm_init", "ba_comm_init_local", "ba_set_params", "ba_get_params", "ba_set_information", "ba_set_fixed",
-    "ba_set_residual_program",
+    "ba_set_residual_program", "ba_residual_program_mode", "ba_residual_program_source",
     "ba_linearize", "ba_process_diag", "ba_solve", "ba_solve_async", "ba_solve_wait",
     "ba_set_params_device", "ba_get_params_device", "ba_step_norms", "ba_eval_trial",
     "ba_accept_step", "ba_reject_step", "ba_grad_inf_norm", "ba_lm_solve", "ba_read", "ba_write_dx",
@@ -97,6 +97,26 @@ def load():
         L.ba_process_diag.restype = C.c_int
         _lib = L
     return _lib
+
+
+def residual_program_source(code, consts, n_slots, out, dtype=np.float64, compile=True):
+    """Host-only: (CUDA source generated for the program, size of the sm_100a image NVRTC built from it or None)."""
+    L = load()
+    code = np.ascontiguousarray(code, np.uint8).reshape(-1, 6)
+    k = np.ascontiguousarray(consts, np.float64)
+    o = np.ascontiguousarray(out, np.int32)
+    n = C.c_int64()
+    cub = C.c_int64()
+    args = (int(code.shape[0]), _p(code), int(k.size), _p(k) if k.size else None, int(n_slots), _p(o),
+            0 if np.dtype(dtype) == np.float64 else 1)
+    rc = L.ba_residual_program_source(*args, None, C.c_int64(0), C.byref(n), None)
+    if rc != 0:
+        raise RuntimeError(f"ba_residual_program_source failed ({rc}): {L.ba_last_error(None).decode()}")
+    buf = C.create_string_buffer(n.value + 1)
+    rc = L.ba_residual_program_source(*args, buf, C.c_int64(n.value + 1), C.byref(n), C.byref(cub) if compile else None)
+    if rc != 0:
+        raise RuntimeError(f"ba_residual_program_source failed ({rc}): {L.ba_last_error(None).decode()}")
+    return buf.value.decode(), (cub.value if compile else None)
 
 
 def partition_points(pt_degree: np.ndarray, world_size: int) -> np.ndarray:
@@ -270,6 +290,10 @@ class Solver:
         o = np.ascontiguousarray(out, np.int32)
         self._chk(self.L.ba_set_residual_program(self.h, int(code.shape[0]), _p(code), int(k.size), _p(k) if k.size else None,
                                                  int(n_slots), _p(o)), "ba_set_residual_program")
+
+    def residual_program_mode(self) -> int:
+        """0 analytical kernels, 1 device interpreter, 2 NVRTC-generated kernels."""
+        return int(self.L.ba_residual_program_mode(self.h))
 
     # -- hot path
     def linearize(self) -> float:

@@ -24,6 +24,7 @@
 #include "ba_internal.h"
 #include "ba_program.cuh"
 #include "ba_program_host.h"
+#include "ba_program_jit.h"
 
 namespace ba {
 
@@ -388,6 +389,7 @@ struct Impl {
   virtual int set_fixed(const unsigned char *cam_fixed, const unsigned char *pt_fixed) = 0;
   virtual int set_residual_program(int n_instr, const uint8_t *code, int n_const, const double *consts, int n_slots,
                                    const int32_t *out_slot) = 0;
+  virtual int residual_program_mode() = 0;
   virtual int linearize(double *cost) = 0;
   virtual int process_diag(double region, int recover) = 0;
   virtual int solve(const ba_pcg_options *o, int *iters, int *done) = 0;
@@ -422,9 +424,14 @@ struct ImplT : Impl {
   unsigned char *cam_fixed_dev = nullptr, *pt_fixed_dev = nullptr;
   uint2 *prog_code_dev = nullptr;  // user-defined residual (ba_set_residual_program)
   T *prog_const_dev = nullptr;
+  cudaLibrary_t jit_lib = nullptr;  // NVRTC-generated kernels of the residual program (ba_program_jit.h)
+  cudaKernel_t jit_fill = nullptr, jit_cost = nullptr;
   T *prog_tab_dev = nullptr;  // frontier tables of the per-camera program (current | trial parameters)
   int *cm_slot_dev = nullptr;
+  int *slot_cm_dev = nullptr;  // generated kernels: inverse of cm_slot, and the camera-major {J camera part, r} copy
+  T *cm_jr_dev = nullptr;
   T *r_slots_dev = nullptr;
+  std::string jit_note;            // why the generated kernels are not in use (empty: they are)
   int store_before_prog = -1;      // the configured stream to go back to when the program is cleared
   double *model_part = nullptr;  // [nW] point partials of the model decrease (left by the back-substitution pass)
   bool model_valid = false;      // scal[S_MODEL_PT / S_MODEL_CAM] describe the step of the last solve
@@ -466,7 +473,10 @@ struct ImplT : Impl {
     if (prog_code_dev) cudaFree(prog_code_dev);
     if (prog_const_dev) cudaFree(prog_const_dev);
     if (cm_slot_dev) cudaFree(cm_slot_dev);
+    if (slot_cm_dev) cudaFree(slot_cm_dev);
+    if (cm_jr_dev) cudaFree(cm_jr_dev);
     if (prog_tab_dev) cudaFree(prog_tab_dev);
+    if (jit_lib) cudaLibraryUnload(jit_lib);
     if (r_slots_dev) cudaFree(r_slots_dev);
     if (pt_fixed_dev) cudaFree(pt_fixed_dev);
     if (pt_full) cudaFree(pt_full);
@@ -924,6 +934,7 @@ struct ImplT : Impl {
       d.prog_code = nullptr;
       d.prog_const = nullptr;
       d.prog_n = 0;
+      d.prog_jit = 0;
       if (store_before_prog >= 0) store_cfg = store_before_prog;
       store_before_prog = -1;
       d.store = store_cfg;
@@ -975,6 +986,69 @@ struct ImplT : Impl {
     store_cfg = ST_J;
     d.store = ST_J;
     linearized = false;
+    // the per-observation program as a kernel of its own (NVRTC); the interpreter stays for ba_eval_edges, for the
+    // per-camera program and as the fallback when NVRTC is not usable on this machine
+    d.prog_jit = 0;
+    jit_fill = jit_cost = nullptr;
+    if (jit_lib) { cudaLibraryUnload(jit_lib); jit_lib = nullptr; }
+    jit_note.clear();
+    const char *je = getenv("BA_PROG_JIT");
+    if (!(je && atoi(je) == 0)) {
+      std::vector<double> kc(consts, consts + n_const);
+      const std::string src = jit_source(P, kc, n_slots, out_slot, sizeof(T) == 8);
+      std::vector<char> cubin;
+      std::string why = jit_compile(src, &cubin);
+      if (why.empty()) {
+        cudaError_t e = cudaLibraryLoadData(&jit_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&jit_fill, jit_lib, "prog_fill");
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&jit_cost, jit_lib, "prog_cost");
+        if (e != cudaSuccess) { why = std::string("loading the generated kernels: ") + cudaGetErrorString(e); cudaGetLastError(); }
+      }
+      if (why.empty() && !slot_cm_dev) {
+        std::vector<int> inv(std::max<size_t>(g.edge_of_slot.size(), 1), -1);
+        for (size_t k = 0; k < g.cm_slot.size(); ++k) inv[g.cm_slot[k]] = (int)k;
+        cudaError_t e = cudaMalloc(&slot_cm_dev, sizeof(int) * inv.size());
+        if (e == cudaSuccess) e = cudaMalloc(&cm_jr_dev, sizeof(T) * 20 * std::max<size_t>(g.cm_slot.size(), 1));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(slot_cm_dev, inv.data(), sizeof(int) * inv.size(), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { why = std::string("buffers of the generated kernels: ") + cudaGetErrorString(e); cudaGetLastError(); }
+        d.slot_cm = slot_cm_dev;
+        d.cm_jr = cm_jr_dev;
+      }
+      if (why.empty()) d.prog_jit = 1;
+      else jit_note = why;  // ba_residual_program_mode reports 1; the reason is kept for ba_last_error
+    }
+    if (!jit_note.empty()) err = "residual program runs in the interpreter: " + jit_note;
+    return BA_OK;
+  }
+
+  int residual_program_mode() override { return !d.prog_code ? 0 : d.prog_jit ? 2 : 1; }
+
+  // r and J of every observation by the generated kernel (before k_lin_ell<PROG> sums them)
+  int jit_fill_stream() {
+    launch_prog_cam<T>(d, 0, stream);
+    if (d.nW > 0) {
+      int nW = d.nW, stride = PROG_FSTRIDE * d.prog_nf;
+      const void *wdesc = d.wdesc, *r_cam = d.r_cam, *r_obs = d.r_obs, *cam = d.cam, *pt = d.pt, *tab = d.prog_tab;
+      void *WJ = d.WJ, *rs = d.r_slots, *cmjr = d.cm_jr;
+      const void *scm = d.slot_cm;
+      void *args[] = {&wdesc, &nW, &r_cam, &r_obs, &cam, &pt, &tab, &stride, &WJ, &rs, &scm, &cmjr};
+      BA_CUDA(cudaLaunchKernel((const void *)jit_fill, dim3((nW + 3) / 4), dim3(128), args, 0, stream));
+    }
+    stats.launches += 2;
+    return BA_OK;
+  }
+  int jit_trial_cost() {
+    launch_prog_cam<T>(d, 1, stream);
+    if (d.nW > 0) {
+      int nW = d.nW, stride = PROG_FSTRIDE * d.prog_nf, pstride = 2;
+      const void *wdesc = d.wdesc, *r_cam = d.r_cam, *r_obs = d.r_obs, *cam = d.cam, *dxc = d.dxc, *pt = d.pt, *dxl = d.dxl,
+                 *tab = d.prog_tab2;
+      void *partials = d.partials;
+      void *args[] = {&wdesc, &nW, &r_cam, &r_obs, &cam, &dxc, &pt, &dxl, &tab, &stride, &partials, &pstride};
+      BA_CUDA(cudaLaunchKernel((const void *)jit_cost, dim3((nW + 3) / 4), dim3(128), args, 0, stream));
+    }
+    stats.launches += 2;
     return BA_OK;
   }
 
@@ -1048,6 +1122,7 @@ struct ImplT : Impl {
     if (timing) ev = ev_begin();
     if (g.ell) {
       d.store = store_cfg;  // the launcher wants the configured store; the one in effect is known after the fetch below
+      if (d.prog_code && d.prog_jit) BA_TRY(jit_fill_stream());
       BA_CUDA(launch_linearize_ell<T>(d, stream));
       stats.launches += launches_of_linearize_ell() - (store_cfg == ST_FACT ? 0 : 1);
     } else {
@@ -1328,6 +1403,7 @@ struct ImplT : Impl {
     }
     if (g.ell) {
       if (d.store == ST_FACT) BA_TRY(pad_cam(d.dxc));  // the factored trial kernel gathers T_c dx_c
+      if (d.prog_code && d.prog_jit) BA_TRY(jit_trial_cost());
       BA_CUDA(launch_trial_ell<T>(d, stream));
     } else {
       BA_CUDA(launch_trial<T>(d, stream));
@@ -1749,6 +1825,36 @@ int ba_set_fixed(ba_solver *s, const uint8_t *cam_fixed, const uint8_t *pt_fixed
 int ba_set_residual_program(ba_solver *s, int32_t n_instr, const uint8_t *code, int32_t n_const, const double *consts,
                             int32_t n_slots, const int32_t *out_slot) {
   BA_FWD(set_residual_program(n_instr, code, n_const, consts, n_slots, out_slot));
+}
+int ba_residual_program_mode(ba_solver *s) { return s && s->impl ? s->impl->residual_program_mode() : BA_ERR_ARG; }
+int ba_residual_program_source(int32_t n_instr, const uint8_t *code, int32_t n_const, const double *consts, int32_t n_slots,
+                               const int32_t *out_slot, int32_t dtype, char *src, int64_t src_cap, int64_t *src_len,
+                               int64_t *cubin_bytes) {
+  using namespace ba;
+  if (n_instr <= 0 || !code || n_const < 0 || (n_const > 0 && !consts) || !out_slot || n_slots < 1 || n_slots > PROG_SLOTS ||
+      (dtype != BA_F64 && dtype != BA_F32)) {
+    g_create_error = "ba_residual_program_source: bad argument";
+    return BA_ERR_ARG;
+  }
+  std::vector<ProgInstr> parsed;
+  int out_def[2];
+  const std::string why = prog_parse(n_instr, code, n_const, n_slots, out_slot, &parsed, out_def);
+  if (!why.empty()) { g_create_error = "residual program: " + why; return BA_ERR_ARG; }
+  const ProgDevice P = prog_lower(parsed, out_def, out_slot, true);
+  const std::string text = jit_source(P, std::vector<double>(consts, consts + n_const), n_slots, out_slot, dtype == BA_F64);
+  if (src_len) *src_len = (int64_t)text.size();
+  if (src && src_cap > 0) {
+    const size_t n = std::min<size_t>(text.size(), (size_t)src_cap - 1);
+    memcpy(src, text.data(), n);
+    src[n] = 0;
+  }
+  if (cubin_bytes) {
+    std::vector<char> cubin;
+    const std::string cw = jit_compile(text, &cubin);
+    if (!cw.empty()) { g_create_error = cw; return BA_ERR_STATE; }
+    *cubin_bytes = (int64_t)cubin.size();
+  }
+  return BA_OK;
 }
 int ba_linearize(ba_solver *s, double *cost) { BA_FWD(linearize(cost)); }
 int ba_process_diag(ba_solver *s, double region, int recover) { BA_FWD(process_diag(region, recover)); }

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(64) k_prog_cam(Dev<T> d, int trial) {
   prog_eval<T, GRAD>(d.prog_cam_code, d.prog_const, d.prog_cam_n, 0, 0, in, (T *)nullptr, (T *)nullptr, (const T *)nullptr, tab);
 }
 template <typename T>
-static void launch_prog_cam(const Dev<T> &d, int trial, cudaStream_t st) {
+void launch_prog_cam(const Dev<T> &d, int trial, cudaStream_t st) {
   if (!d.prog_code || d.prog_cam_n == 0 || d.nC == 0) return;
   if (trial) k_prog_cam<T, false><<<(d.nC + 63) / 64, 64, 0, st>>>(d, 1);
   else k_prog_cam<T, true><<<(d.nC + 63) / 64, 64, 0, st>>>(d, 0);
@@ -221,10 +221,16 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
     } else {
       T J[24];
       if (PROG) {
-        prog_edge<T, true>(d, c, d.prog_tab, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
-        typename Vec2<T>::type rv;
-        rv.x = r0; rv.y = r1;
-        reinterpret_cast<typename Vec2<T>::type *>(d.r_slots)[slot] = rv;
+        if (d.prog_jit) {  // the generated kernel (prog_fill) left r and J; here they only enter the sums
+          load_stream<T, 24>(d.WJ, row, lane, J);
+          const typename Vec2<T>::type rv = reinterpret_cast<const typename Vec2<T>::type *>(d.r_slots)[slot];
+          r0 = rv.x; r1 = rv.y;
+        } else {
+          prog_edge<T, true>(d, c, d.prog_tab, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+          typename Vec2<T>::type rv;
+          rv.x = r0; rv.y = r1;
+          reinterpret_cast<typename Vec2<T>::type *>(d.r_slots)[slot] = rv;
+        }
       } else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
       if (pfixed) {
 #pragma unroll
@@ -234,7 +240,8 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
 #pragma unroll
         for (int q = 0; q < 9; ++q) J[q] = J[12 + q] = T(0);
       }
-      store_stream<T, K>(d.WJ, row, lane, J);
+      // the generated kernel already wrote the stream; it only changes here when a vertex is fixed
+      if (!(PROG && d.prog_jit) || d.cam_fixed || d.pt_fixed) store_stream<T, K>(d.WJ, row, lane, J);
 #pragma unroll
       for (int q = 0; q < 3; ++q) { Jp[q] = J[9 + q]; Jp[3 + q] = J[21 + q]; }
     }
@@ -1216,9 +1223,10 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
     a_model += (double)((m0 + r0) * (m0 + r0)) + (double)((m1 + r1) * (m1 + r1));
 #pragma unroll
     for (int k = 0; k < 9; ++k) cm[k] += dc[k];  // updateDeltaXTwoVertices, update.cu:14-41
-    T s0, s1;
-    if (PROG) prog_edge<T, false>(d, c, d.prog_tab2, cm, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1, (T *)nullptr);
-    else {
+    T s0 = T(0), s1 = T(0);
+    if (PROG) {
+      if (!d.prog_jit) prog_edge<T, false>(d, c, d.prog_tab2, cm, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1, (T *)nullptr);
+    } else {
       rc = rot_const<T>(cm[0], cm[1], cm[2]);
       edge_residual<T>(cm, rc, X0 + D0, X1 + D1, X2 + D2, ob.x, ob.y, s0, s1);
     }
@@ -1227,7 +1235,7 @@ __global__ void __launch_bounds__(ELL_THREADS) k_trial_ell(Dev<T> d) {
   a_cost = warp_sum<double>(a_cost);
   a_model = warp_sum<double>(a_model);
   if (lane == 0) {
-    d.partials[2 * (size_t)w] = a_cost;
+    if (!(PROG && d.prog_jit)) d.partials[2 * (size_t)w] = a_cost;  // else: written by the generated prog_cost kernel
     d.partials[2 * (size_t)w + 1] = a_model;
   }
 }
@@ -1561,7 +1569,7 @@ cudaError_t launch_linearize_ell(const Dev<T> &d, cudaStream_t st) {
       launch_lin_ell_s<T, ST_FACT>(d, 1, st);
       launch_lin_ell_s<T, ST_J>(d, 2, st);
     } else if (d.prog_code) {  // user-defined residual: the interpreter fills the Jacobian stream
-      launch_prog_cam<T>(d, 0, st);
+      if (!d.prog_jit) launch_prog_cam<T>(d, 0, st);
       if (d.r_info) k_lin_ell<T, ST_J, true, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
       else k_lin_ell<T, ST_J, false, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
     } else {
@@ -1761,7 +1769,7 @@ cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st) {
     if (d.nW > 0) k_trial_fact<T><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
   } else if (d.nW > 0) {
     if (d.prog_code) {
-      launch_prog_cam<T>(d, 1, st);
+      if (!d.prog_jit) launch_prog_cam<T>(d, 1, st);
       k_trial_ell<T, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
     }
     else k_trial_ell<T, false><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d);
@@ -1815,6 +1823,7 @@ cudaError_t launch_permute3(const T *src, T *dst, const int *perm, int n, int ga
   template cudaError_t launch_schur_ell<T>(const Dev<T> &, int, const T *, T *, T *, int, cudaStream_t);      \
   template cudaError_t launch_prep_ell<T>(const Dev<T> &, cudaStream_t);                                      \
   template cudaError_t launch_trial_ell<T>(const Dev<T> &, cudaStream_t);                                     \
+  template void launch_prog_cam<T>(const Dev<T> &, int, cudaStream_t);                                        \
   template cudaError_t launch_trial_cost_ell<T>(const Dev<T> &, cudaStream_t);                                \
   template cudaError_t launch_model_terms<T>(const Dev<T> &, cudaStream_t);                                   \
   template cudaError_t launch_eval_edges_ell<T>(const Dev<T> &, T *, T *, cudaStream_t);                      \

@@ -115,9 +115,13 @@ struct Dev {
   const uint2 *prog_cam_code;  // camera-only part, run once per camera (k_prog_cam); fills prog_tab
   int prog_cam_n, prog_nf;     // its length; frontier values per camera
   T *prog_tab, *prog_tab2;     // [nC][prog_nf][10] at the current / at the trial parameters
+  int prog_jit;                // 1: r, J and the trial cost come from the NVRTC-generated kernels (ba_program_jit.h); the
+                               // PROG flavours below then only read the stream / the residual array
   int split;           // warps sharing one slice in the S*p pass (1, 2 or 4; ImplT::init chooses by the shard's size)
   const int *cm_slot;  // [nEl] slot of each camera-major entry: the camera side reads r and J the point side left
   T *r_slots;          // [nSlots][2] residuals of the current linearisation
+  const int *slot_cm;  // [nSlots] inverse of cm_slot (-1: empty slot), generated kernels only
+  T *cm_jr;            // [nEl][20] camera-major copy {J row 0 camera part, J row 1 camera part, r} written by prog_fill
   // camera-major static graph
   const int4 *chunk;            // {cam, beg, end, 0}
   const int *cam_chunk_ptr;     // [nC+1]
@@ -186,6 +190,7 @@ template <typename T> cudaError_t launch_schur_ell(const Dev<T> &d, int mode, co
                                                    int check_active, cudaStream_t st);
 template <typename T> cudaError_t launch_prep_ell(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st);
+template <typename T> void launch_prog_cam(const Dev<T> &d, int trial, cudaStream_t st);
 template <typename T> cudaError_t launch_trial_cost_ell(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_model_terms(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_eval_edges_ell(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st);

@@ -183,7 +183,23 @@ __global__ void __launch_bounds__(CM_THREADS, 3) k_lin_cm(Dev<T> d, int dispatch
   for (int k = 0; k < NTRI + 9; ++k) acc[k] = T(0);
   for (int k = beg + (int)threadIdx.x; k < end; k += CM_THREADS) {
     T J[24], r0, r1;
-    if (PROG) {  // user-defined residual: read what the point-side pass (k_lin_ell) evaluated, from its row-blocked stream
+    if (PROG && d.prog_jit) {  // the generated kernel left a camera-major copy of what this pass needs: 160 contiguous bytes
+      using V = typename Vec2<T>::type;
+      const V *src = reinterpret_cast<const V *>(d.cm_jr) + 10 * (size_t)k;
+      T v[20];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const V x = __ldg(src + j);
+        v[2 * j] = x.x;
+        v[2 * j + 1] = x.y;
+      }
+      const bool cfix = d.cam_fixed && d.cam_fixed[c];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { J[q] = cfix ? T(0) : v[q]; J[12 + q] = cfix ? T(0) : v[9 + q]; }
+#pragma unroll
+      for (int q = 9; q < 12; ++q) J[q] = J[12 + q] = T(0);  // the point columns play no part on the camera side
+      r0 = v[18]; r1 = v[19];
+    } else if (PROG) {  // interpreter: read what the point-side pass (k_lin_ell) evaluated, from its row-blocked stream
       using V = typename Vec2<T>::type;
       const int slot = d.cm_slot[k];
       const V *src = reinterpret_cast<const V *>(d.WJ) + (size_t)(slot >> 5) * (12 * 32) + (slot & 31);

@@ -17,6 +17,10 @@ from residual_program import trace_bal_edge
 P = make_named(sys.argv[1] if len(sys.argv) > 1 else "venice-1778")
 prog = trace_bal_edge(tempfile.mkdtemp())
 print(f"program: {len(prog['code'])} instructions, {prog['n_slots']} registers", flush=True)
+_warm = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs)  # context, module loading, allocator: not part of any line below
+_warm.set_params(P.cam, P.pt)
+_warm.lm_solve(lm_max_iter=2, initial_region=1e4, eps1=-1, eps2=-1, pcg_max_iter=5, pcg_tol=1e-2)
+_warm.close()
 for dtype in (np.float64, np.float32):
     for name, pr in (("analytical", None), ("program", prog)):
         S = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype=dtype)
@@ -41,6 +45,7 @@ for dtype in (np.float64, np.float32):
         t0 = time.perf_counter()
         tr = S.lm_solve(lm_max_iter=10, initial_region=1e4, eps1=-1, eps2=-1, pcg_max_iter=30, pcg_tol=1e-2)
         dt = time.perf_counter() - t0
-        print(f"{np.dtype(dtype).name:8s} {name:10s} linearise {st['linearize_ms']/st['linearize_calls']:8.3f} ms   trial {tt*1e3:7.3f} ms   "
+        name = name + {0: "", 1: "/interp", 2: "/jit"}[S.residual_program_mode()]
+        print(f"{np.dtype(dtype).name:8s} {name:14s} linearise {st['linearize_ms']/st['linearize_calls']:8.3f} ms   trial {tt*1e3:7.3f} ms   "
               f"cost {c:.6e}   LM {len(tr)-1} it in {dt*1e3:7.1f} ms  final {tr[-1]['cost']:.6e}", flush=True)
         S.close()

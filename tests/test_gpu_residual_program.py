@@ -13,15 +13,25 @@ from megba_b200 import capi
 from megba_b200.synthetic import make_synthetic, read_bal, write_bal
 from oracle.oracle import Oracle
 from residual_program import BIN, build_examples, edge_inputs, eval_program, trace_bal_edge
-from util import rel_fro
+from util import bal_like_problem, rel_fro
 
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["jit", "interpreter"])
+def evaluation_mode(request, monkeypatch):
+    """Every test runs twice: with the NVRTC-generated kernels (the default) and with the device interpreter."""
+    monkeypatch.setenv("BA_PROG_JIT", "1" if request.param == "jit" else "0")
+    return 2 if request.param == "jit" else 1
+
+
 def _solver(P, dtype=np.float64, prog=None, **kw):
     S = capi.Solver(P.nC, P.nP, P.cam_idx, P.pt_idx, P.obs, dtype=dtype, **kw)
+    assert S.residual_program_mode() == 0
     if prog is not None:
         S.set_residual_program(prog["code"], prog["consts"], prog["n_slots"], prog["out"])
+        want = 2 if os.environ.get("BA_PROG_JIT") != "0" else 1
+        assert S.residual_program_mode() == want, S.L.ba_last_error(S.h).decode()
     S.set_params(P.cam, P.pt)
     return S
 
@@ -74,6 +84,29 @@ def test_linearisation_and_lm_match_the_analytical_kernels(tmp_path, info):
     assert np.allclose([t["cost"] for t in a["tr"]], [t["cost"] for t in b["tr"]], rtol=1e-8)
     assert rel_fro(b["cam"], a["cam"]) <= 1e-7 and rel_fro(b["pt"], a["pt"]) <= 1e-7
     assert b["tr"][-1]["cost"] < 0.5 * b["tr"][0]["cost"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_heavy_tailed_graph(tmp_path, dtype):
+    """Points with a warp of their own (more than 32 observations) and slices of every height, both precisions."""
+    prog = trace_bal_edge(tmp_path)
+    P = bal_like_problem()
+    tol = 1e-10 if dtype == np.float64 else 2e-4
+    out = []
+    for pr in (None, prog):
+        S = _solver(P, dtype, pr)
+        cost = S.linearize()
+        bufs = [S.read(w) for w in (capi.BUF_HPP, capi.BUF_HLL, capi.BUF_G)]
+        S.process_diag(1e3)
+        S.solve(max_iter=8, tol=0.0, refuse_ratio=1e300)
+        out.append((cost, bufs, S.read(capi.BUF_DX), S.eval_trial()))
+        S.close()
+    (ca, ba_, dxa, ta), (cb, bb, dxb, tb) = out
+    assert abs(ca - cb) <= tol * ca
+    for x, y in zip(ba_, bb):
+        assert rel_fro(y, x) <= tol
+    assert rel_fro(dxb, dxa) <= (1e-7 if dtype == np.float64 else 5e-3)
+    assert abs(ta[0] - tb[0]) <= (1e-9 if dtype == np.float64 else 1e-3) * ta[0]
 
 
 def test_program_can_be_cleared_and_fixed_vertices_apply(tmp_path):

@@ -6,6 +6,7 @@ import numpy as np
 
 from megba_b200.synthetic import make_synthetic
 from oracle.oracle import Oracle
+from megba_b200 import capi
 from residual_program import OPS, edge_inputs, eval_program, trace_bal_edge
 from util import rel_fro
 
@@ -41,3 +42,23 @@ def test_compiler_reuses_registers_and_drops_dead_code(tmp_path):
         live.discard(dst)
         live.update(src[:nsrc.get(op, 2)])
     assert not live
+
+
+def test_generated_kernel_source_compiles_for_sm_100a(tmp_path):
+    """ba_residual_program_source (host-only): the per-observation program printed as straight-line CUDA C++ and built
+    by NVRTC for sm_100a -- no GPU needed.  The rotation is not in the per-observation kernel (it runs once per
+    camera), derivative groups that are identically zero are not printed."""
+    import pytest
+    prog = trace_bal_edge(tmp_path)
+    for dtype in (np.float64, np.float32):
+        src, cubin = capi.residual_program_source(prog["code"], prog["consts"], prog["n_slots"], prog["out"], dtype)
+        assert cubin > 1000
+        assert 'extern "C" __global__' in src and "prog_fill" in src and "prog_cost" in src
+        assert ("typedef double T;" in src) == (dtype == np.float64)
+        body = src[src.index("prog_fill"):src.index("prog_cost")]
+        assert "sincos" not in body and "tabc[" in body      # angle-axis -> rotation happens per camera
+        assert body.count("// ") < len(prog["code"])          # fewer statements than the caller's program
+    bad = prog["code"].copy()
+    bad[5, 0] = 99
+    with pytest.raises(RuntimeError, match="unknown op"):
+        capi.residual_program_source(bad, prog["consts"], prog["n_slots"], prog["out"])
