@@ -102,8 +102,9 @@ def peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons of one GPU, sampled DURING the timed regions.  NVML in a thread of this process
-    (the library nvidia-smi itself reads; a sample every 5 ms, so that even the 30 ms timed region of an 8-GPU run gets
-    several), `nvidia-smi -lms 25` in a subprocess when the NVML binding is not importable."""
+    (the library nvidia-smi itself reads; a sample every 20 ms (BENCH_CLOCK_MS): the 30 ms + 45 ms timed regions of an
+    8-GPU run still get a few, and four 4-GPU runs showed no effect on the timings at 50 ms and one slower camera/exchange
+    kernel in two runs at 5 ms), `nvidia-smi -lms 25` in a subprocess when the NVML binding is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -117,6 +118,7 @@ class ClockSampler:
         self.samples = []   # (sm_mhz, reasons_bitmask)
         self.max_mhz = None
         self.running = False
+        self.period = float(os.environ.get("BENCH_CLOCK_MS", "20")) * 1e-3
 
     def _nvml_loop(self, nv, h):
         while self.running:
@@ -129,7 +131,7 @@ class ClockSampler:
                 self.samples.append((float(sm), int(why)))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(self.period)
 
     def start(self):
         try:
