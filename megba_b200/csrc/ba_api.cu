@@ -1024,15 +1024,16 @@ struct ImplT : Impl {
 
   int residual_program_mode() override { return !d.prog_code ? 0 : d.prog_jit ? 2 : 1; }
 
-  // r and J of every observation by the generated kernel (before k_lin_ell<PROG> sums them)
+  // the point side of the linearisation by the generated kernel (in place of k_lin_ell<PROG>)
   int jit_fill_stream() {
     launch_prog_cam<T>(d, 0, stream);
     if (d.nW > 0) {
       int nW = d.nW, stride = PROG_FSTRIDE * d.prog_nf;
       const void *wdesc = d.wdesc, *r_cam = d.r_cam, *r_obs = d.r_obs, *cam = d.cam, *pt = d.pt, *tab = d.prog_tab;
-      void *WJ = d.WJ, *rs = d.r_slots, *cmjr = d.cm_jr;
-      const void *scm = d.slot_cm;
-      void *args[] = {&wdesc, &nW, &r_cam, &r_obs, &cam, &pt, &tab, &stride, &WJ, &rs, &scm, &cmjr};
+      void *WJ = d.WJ, *rs = d.r_slots, *cmjr = d.cm_jr, *Hll = d.Hll, *gl = d.gl, *partials = d.partials;
+      const void *scm = d.slot_cm, *info = d.r_info, *cfix = d.cam_fixed, *pfix = d.pt_fixed;
+      void *args[] = {&wdesc, &nW, &r_cam, &r_obs, &cam, &pt, &tab, &stride, &WJ, &rs, &scm, &cmjr, &info, &cfix, &pfix, &Hll, &gl,
+                      &partials};
       BA_CUDA(cudaLaunchKernel((const void *)jit_fill, dim3((nW + 3) / 4), dim3(128), args, 0, stream));
     }
     stats.launches += 2;

@@ -220,17 +220,11 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
       for (int k = 0; k < 6; ++k) Jp[k] = sv[k];
     } else {
       T J[24];
-      if (PROG) {
-        if (d.prog_jit) {  // the generated kernel (prog_fill) left r and J; here they only enter the sums
-          load_stream<T, 24>(d.WJ, row, lane, J);
-          const typename Vec2<T>::type rv = reinterpret_cast<const typename Vec2<T>::type *>(d.r_slots)[slot];
-          r0 = rv.x; r1 = rv.y;
-        } else {
-          prog_edge<T, true>(d, c, d.prog_tab, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
-          typename Vec2<T>::type rv;
-          rv.x = r0; rv.y = r1;
-          reinterpret_cast<typename Vec2<T>::type *>(d.r_slots)[slot] = rv;
-        }
+      if (PROG) {  // interpreter flavour (the generated prog_fill kernel replaces this whole kernel, ba_program_jit.h)
+        prog_edge<T, true>(d, c, d.prog_tab, cm, X0, X1, X2, ob.x, ob.y, r0, r1, J);
+        typename Vec2<T>::type rv;
+        rv.x = r0; rv.y = r1;
+        reinterpret_cast<typename Vec2<T>::type *>(d.r_slots)[slot] = rv;
       } else edge_residual_jacobian<T>(cm, rc, X0, X1, X2, ob.x, ob.y, r0, r1, J);
       if (pfixed) {
 #pragma unroll
@@ -240,8 +234,7 @@ __global__ void __launch_bounds__(ELL_THREADS) k_lin_ell(Dev<T> d, int dispatch)
 #pragma unroll
         for (int q = 0; q < 9; ++q) J[q] = J[12 + q] = T(0);
       }
-      // the generated kernel already wrote the stream; it only changes here when a vertex is fixed
-      if (!(PROG && d.prog_jit) || d.cam_fixed || d.pt_fixed) store_stream<T, K>(d.WJ, row, lane, J);
+      store_stream<T, K>(d.WJ, row, lane, J);
 #pragma unroll
       for (int q = 0; q < 3; ++q) { Jp[q] = J[9 + q]; Jp[3 + q] = J[21 + q]; }
     }
@@ -1569,9 +1562,11 @@ cudaError_t launch_linearize_ell(const Dev<T> &d, cudaStream_t st) {
       launch_lin_ell_s<T, ST_FACT>(d, 1, st);
       launch_lin_ell_s<T, ST_J>(d, 2, st);
     } else if (d.prog_code) {  // user-defined residual: the interpreter fills the Jacobian stream
-      if (!d.prog_jit) launch_prog_cam<T>(d, 0, st);
-      if (d.r_info) k_lin_ell<T, ST_J, true, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
-      else k_lin_ell<T, ST_J, false, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
+      if (!d.prog_jit) {  // else: the generated prog_fill kernel has done the point side (ImplT::jit_fill_stream)
+        launch_prog_cam<T>(d, 0, st);
+        if (d.r_info) k_lin_ell<T, ST_J, true, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
+        else k_lin_ell<T, ST_J, false, true><<<ell_grid(d.nW), ELL_THREADS, 0, st>>>(d, 0);
+      }
     } else {
       launch_lin_ell_s<T, ST_J>(d, 0, st);
     }

@@ -115,8 +115,8 @@ struct Dev {
   const uint2 *prog_cam_code;  // camera-only part, run once per camera (k_prog_cam); fills prog_tab
   int prog_cam_n, prog_nf;     // its length; frontier values per camera
   T *prog_tab, *prog_tab2;     // [nC][prog_nf][10] at the current / at the trial parameters
-  int prog_jit;                // 1: r, J and the trial cost come from the NVRTC-generated kernels (ba_program_jit.h); the
-                               // PROG flavours below then only read the stream / the residual array
+  int prog_jit;                // 1: the point side of the linearisation and the trial cost run in the NVRTC-generated
+                               // kernels (ba_program_jit.h); k_lin_cm<PROG> / k_trial_ell<PROG> read what they left
   int split;           // warps sharing one slice in the S*p pass (1, 2 or 4; ImplT::init chooses by the shard's size)
   const int *cm_slot;  // [nEl] slot of each camera-major entry: the camera side reads r and J the point side left
   T *r_slots;          // [nSlots][2] residuals of the current linearisation

@@ -10,9 +10,9 @@
 // (12+1) x nE slab per JetVector operator (src/operator/jet_vector_math_impl.cu).
 //
 // Two kernels are generated:
-//   prog_fill  r and J of every observation of the ELL layout -> Jacobian stream (row-blocked, as k_lin_ell writes it),
-//              residual array and a camera-major copy of the camera part; k_lin_ell<..., PROG> / k_lin_cm<PROG> build
-//              the normal equations from them.
+//   prog_fill  the point side of the linearisation (what k_lin_ell does for the built-in residual): r and J of every
+//              observation -> Jacobian stream, residual array, camera-major copy of the camera part for k_lin_cm<PROG>;
+//              Hll, g_l and the cost as thread-local sums.
 //   prog_cost  sum of squared residuals at the trial point (cam + dx_c, pt + dx_l), one partial per warp.
 // NVRTC needs no GPU: ba_residual_program_source (host-only) returns the source and compiles it, which is how the
 // CPU test suite checks the generator.
@@ -161,10 +161,18 @@ __device__ __forceinline__ double warp_sum(double v) {
   const std::string o0 = std::to_string(out_slot[0]), o1 = std::to_string(out_slot[1]);
   // ---- prog_fill
   s += R"(
-// one warp per slice (lane = point) or per heavy point (lane = observation), as k_lin_ell (ba_ell.cu)
+template <typename X> __device__ __forceinline__ X warp_sum_t(X v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// One warp per slice (lane = point) or per heavy point (lane = observation): the whole point side of the linearisation,
+// as k_lin_ell (ba_ell.cu) does it for the built-in residual -- r, J -> Jacobian stream, residual array, camera-major
+// copy of the camera part; Hll, g_l and the cost as thread-local sums (fixed vertices and information matrices included).
 extern "C" __global__ void __launch_bounds__(128) prog_fill(const int4 *__restrict__ wdesc, int nW, const int *__restrict__ r_cam,
     const T2 *__restrict__ r_obs, const T *__restrict__ cam, const T *__restrict__ pt, const T *__restrict__ tab, int tab_stride,
-    T2 *__restrict__ WJ, T2 *__restrict__ r_slots, const int *__restrict__ slot_cm, T2 *__restrict__ cm_jr) {
+    T2 *__restrict__ WJ, T2 *__restrict__ r_slots, const int *__restrict__ slot_cm, T2 *__restrict__ cm_jr,
+    const T *__restrict__ r_info, const unsigned char *__restrict__ cam_fixed, const unsigned char *__restrict__ pt_fixed,
+    T *__restrict__ Hll, T *__restrict__ gl, double *__restrict__ partials) {
   const int lane = threadIdx.x & 31, w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= nW) return;
   const int4 dv = wdesc[w];
@@ -173,6 +181,11 @@ extern "C" __global__ void __launch_bounds__(128) prog_fill(const int4 *__restri
   const bool pvalid = heavy || lane < np;
   T in9 = T(0), in10 = T(0), in11 = T(0);
   if (pvalid) { in9 = pt[3 * (size_t)p]; in10 = pt[3 * (size_t)p + 1]; in11 = pt[3 * (size_t)p + 2]; }
+  const bool pfixed = pvalid && pt_fixed && pt_fixed[p];
+  T hl[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) hl[k] = T(0);
+  double cost = 0.;
   for (int r = 0; r < D; ++r) {
     const size_t row = (size_t)row0 + r, slot = row * 32 + lane;
     const int c = r_cam[slot];
@@ -186,25 +199,71 @@ extern "C" __global__ void __launch_bounds__(128) prog_fill(const int4 *__restri
     DECLARE_REGS;
 )";
   s += jit_body(D.obs_code, consts, true, f64);
-  s += "    T2 *dst = WJ + row * (size_t)(12 * 32) + lane;\n";
-  for (int j = 0; j < 12; ++j) {
-    const int k0 = 2 * j, k1 = 2 * j + 1;  // J[24] = row 0 partials 0..11, row 1 partials 0..11
-    auto g = [&](int k) { return "g" + (k < 12 ? o0 : o1) + "_" + std::to_string(k % 12); };
-    s += "    { T2 x; x.x = " + g(k0) + "; x.y = " + g(k1) + "; dst[" + std::to_string(j) + " * 32] = x; }\n";
+  s += "    T J[24];\n";
+  for (int k = 0; k < 24; ++k) s += "    J[" + std::to_string(k) + "] = g" + (k < 12 ? o0 : o1) + "_" + std::to_string(k % 12) + ";\n";
+  s += "    const T r0 = v" + o0 + ", r1 = v" + o1 + ";\n";
+  s += R"(
+    {  // camera-major copy for the camera side (k_lin_cm, which drops the columns of a fixed camera itself)
+      T2 *cm = cm_jr + 10 * (size_t)slot_cm[slot];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { T2 x; x.x = J[2 * j]; x.y = J[2 * j + 1]; cm[j] = x; }
+      { T2 x; x.x = J[8]; x.y = J[12]; cm[4] = x; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { T2 x; x.x = J[13 + 2 * j]; x.y = J[14 + 2 * j]; cm[5 + j] = x; }
+      { T2 x; x.x = r0; x.y = r1; cm[9] = x; }
+    }
+    if (pfixed) {  // a fixed vertex has no columns
+#pragma unroll
+      for (int q = 0; q < 3; ++q) J[9 + q] = J[21 + q] = T(0);
+    }
+    if (cam_fixed && cam_fixed[c]) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) J[q] = J[12 + q] = T(0);
+    }
+    T2 *dst = WJ + row * (size_t)(12 * 32) + lane;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { T2 x; x.x = J[2 * j]; x.y = J[2 * j + 1]; dst[j * 32] = x; }
+    { T2 x; x.x = r0; x.y = r1; r_slots[slot] = x; }
+    cost += (double)(r0 * r0) + (double)(r1 * r1);
+    T Jp[6], L[6];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { Jp[q] = J[9 + q]; Jp[3 + q] = J[21 + q]; }
+    if (r_info) {  // Omega-weighted rows (JMulInfo)
+      const T om0 = r_info[4 * slot], om1 = r_info[4 * slot + 1], om2 = r_info[4 * slot + 2], om3 = r_info[4 * slot + 3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        L[q] = Jp[q] * om0 + Jp[3 + q] * om2;
+        L[3 + q] = Jp[q] * om1 + Jp[3 + q] * om3;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) L[q] = Jp[q];
+    }
+#pragma unroll
+    for (int y = 0; y < 3; ++y) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) hl[3 * y + q] += L[y] * Jp[q] + L[3 + y] * Jp[3 + q];
+      hl[9 + y] -= L[y] * r0 + L[3 + y] * r1;
+    }
   }
-  s += "    { T2 x; x.x = v" + o0 + "; x.y = v" + o1 + "; r_slots[slot] = x; }\n";
-  // camera-major copy for the camera side of the linearisation (k_lin_cm): {J row 0 [0..8], J row 1 [0..8], r}
-  s += "    T2 *cm = cm_jr + 10 * (size_t)slot_cm[slot];\n";
-  {
-    std::vector<std::string> e;
-    for (int k = 0; k < 9; ++k) e.push_back("g" + o0 + "_" + std::to_string(k));
-    for (int k = 0; k < 9; ++k) e.push_back("g" + o1 + "_" + std::to_string(k));
-    e.push_back("v" + o0);
-    e.push_back("v" + o1);
-    for (int j = 0; j < 10; ++j)
-      s += "    { T2 x; x.x = " + e[2 * j] + "; x.y = " + e[2 * j + 1] + "; cm[" + std::to_string(j) + "] = x; }\n";
+  if (heavy) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) hl[k] = warp_sum_t<T>(hl[k]);
   }
-  s += "  }\n}\n";
+  if (pvalid && (!heavy || lane == 0)) {
+    if (pfixed) {  // identity block, zero gradient: dx_l = 0
+#pragma unroll
+      for (int k = 0; k < 9; ++k) hl[k] = (k % 4 == 0) ? T(1) : T(0);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hll[9 * (size_t)p + k] = hl[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gl[3 * (size_t)p + k] = hl[9 + k];
+  }
+  cost = warp_sum(cost);
+  if (lane == 0) partials[w] = cost;
+}
+)";
   // ---- prog_cost
   s += R"(
 extern "C" __global__ void __launch_bounds__(128) prog_cost(const int4 *__restrict__ wdesc, int nW, const int *__restrict__ r_cam,
