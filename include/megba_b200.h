@@ -218,8 +218,9 @@ int ba_set_fixed(ba_solver *s, const uint8_t *cam_fixed, const uint8_t *pt_fixed
 
 /* User-defined residuals: the reference's plug-in seam BaseEdge::forward() on JetVectors (include/edge/base_edge.h:43,
  * include/operator/jet_vector.h:23-171, one kernel launch per operator).  Here the residual is a register bytecode --
- * the facade records forward() once on a tape and compiles it (include/megba/operator/jet_vector.h) -- that the library
- * evaluates per observation with forward-mode automatic differentiation in one fused kernel; the Jacobians go into the
+ * the facade records forward() once on a tape and compiles it (include/megba/operator/jet_vector.h) -- from which the
+ * library generates ONE fused kernel (forward-mode automatic differentiation written out as straight-line code, built
+ * with NVRTC for this GPU; a device interpreter of the same program is the fallback).  The Jacobians go into the
  * Jacobian operator stream, everything downstream (assembly, Schur PCG, LM) is the path of the built-in residual.
  *   code[n_instr][6] = {op, dst, a, b, c, d} (register numbers < n_slots <= BA_PROGRAM_MAX_SLOTS);
  *   ops: 0 INPUT (a = input: 0..8 camera, 9..11 point, 12..13 observation), 1 CONST (a = index into consts),
