@@ -1125,7 +1125,10 @@ struct ImplT : Impl {
       d.store = store_cfg;  // the launcher wants the configured store; the one in effect is known after the fetch below
       if (d.prog_code && d.prog_jit) BA_TRY(jit_fill_stream());
       BA_CUDA(launch_linearize_ell<T>(d, stream));
-      stats.launches += launches_of_linearize_ell() - (store_cfg == ST_FACT ? 0 : 1);
+      // factored store: both point-side flavours + both camera-side flavours (device-side dispatch) + the cost reduction;
+      // Jacobian store: k_lin_ell, k_lin_cm, k_lin_cam_reduce, k_reduce; a residual program adds k_prog_cam (interpreter) or
+      // replaces k_lin_ell by the generated kernel (counted in jit_fill_stream)
+      stats.launches += store_cfg == ST_FACT ? launches_of_linearize_ell() : 4 + (d.prog_code ? (d.prog_jit ? -1 : 1) : 0);
     } else {
       BA_CUDA(launch_linearize<T>(d, stream));
       stats.launches += launches_of_linearize();
