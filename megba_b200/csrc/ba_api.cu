@@ -1029,7 +1029,7 @@ struct ImplT : Impl {
     launch_prog_cam<T>(d, 0, stream);
     if (d.nW > 0) {
       int nW = d.nW, stride = PROG_FSTRIDE * d.prog_nf;
-      const void *wdesc = d.wdesc, *r_cam = d.r_cam, *r_obs = d.r_obs, *cam = d.cam, *pt = d.pt, *tab = d.prog_tab;
+      const void *wdesc = d.wdesc, *r_cam = d.r_cam, *r_obs = d.r_obs, *cam = d.camc, *pt = d.pt, *tab = d.prog_tab;
       void *WJ = d.WJ, *rs = d.r_slots, *cmjr = d.cm_jr, *Hll = d.Hll, *gl = d.gl, *partials = d.partials;
       const void *scm = d.slot_cm, *info = d.r_info, *cfix = d.cam_fixed, *pfix = d.pt_fixed;
       void *args[] = {&wdesc, &nW, &r_cam, &r_obs, &cam, &pt, &tab, &stride, &WJ, &rs, &scm, &cmjr, &info, &cfix, &pfix, &Hll, &gl,
@@ -1043,10 +1043,10 @@ struct ImplT : Impl {
     launch_prog_cam<T>(d, 1, stream);
     if (d.nW > 0) {
       int nW = d.nW, stride = PROG_FSTRIDE * d.prog_nf, pstride = 2;
-      const void *wdesc = d.wdesc, *r_cam = d.r_cam, *r_obs = d.r_obs, *cam = d.cam, *dxc = d.dxc, *pt = d.pt, *dxl = d.dxl,
-                 *tab = d.prog_tab2;
+      // camc2: the trial cameras cam + dx_c, written by k_prog_cam just above
+      const void *wdesc = d.wdesc, *r_cam = d.r_cam, *r_obs = d.r_obs, *cam = d.camc2, *pt = d.pt, *dxl = d.dxl, *tab = d.prog_tab2;
       void *partials = d.partials;
-      void *args[] = {&wdesc, &nW, &r_cam, &r_obs, &cam, &dxc, &pt, &dxl, &tab, &stride, &partials, &pstride};
+      void *args[] = {&wdesc, &nW, &r_cam, &r_obs, &cam, &pt, &dxl, &tab, &stride, &partials, &pstride};
       BA_CUDA(cudaLaunchKernel((const void *)jit_cost, dim3((nW + 3) / 4), dim3(128), args, 0, stream));
     }
     stats.launches += 2;

@@ -162,12 +162,16 @@ __global__ void __launch_bounds__(64) k_prog_cam(Dev<T> d, int trial) {
   for (int k = 0; k < 9; ++k) in[k] = d.cam[9 * (size_t)c + k] + (trial ? d.dxc[9 * (size_t)c + k] : T(0));
 #pragma unroll
   for (int k = 9; k < PROG_NIN; ++k) in[k] = T(0);
+  if (trial) {  // the trial camera, in 16-byte aligned rows for the generated prog_cost kernel
+#pragma unroll
+    for (int k = 0; k < 9; ++k) d.camc2[(size_t)CAMC * c + k] = in[k];
+  }
   T *tab = (trial ? d.prog_tab2 : d.prog_tab) + (size_t)c * (PROG_FSTRIDE * d.prog_nf);
   prog_eval<T, GRAD>(d.prog_cam_code, d.prog_const, d.prog_cam_n, 0, 0, in, (T *)nullptr, (T *)nullptr, (const T *)nullptr, tab);
 }
 template <typename T>
 void launch_prog_cam(const Dev<T> &d, int trial, cudaStream_t st) {
-  if (!d.prog_code || d.prog_cam_n == 0 || d.nC == 0) return;
+  if (!d.prog_code || d.nC == 0) return;
   if (trial) k_prog_cam<T, false><<<(d.nC + 63) / 64, 64, 0, st>>>(d, 1);
   else k_prog_cam<T, true><<<(d.nC + 63) / 64, 64, 0, st>>>(d, 0);
 }

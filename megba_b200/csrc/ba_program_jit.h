@@ -118,12 +118,18 @@ inline std::string jit_body(const std::vector<uint2> &code, const std::vector<do
         nv = V(w.a);
         for (int k = 0; k < 12; ++k) if (!has(w.ma, k)) ng[k] = "T(0)";  // the groups it had stay as they are
         break;
-      case P_LOADF:
-        snprintf(buf, sizeof buf, "tabc[%d]", PROG_FSTRIDE * w.a);
-        nv = buf;
-        for (int k = 0; k < 9; ++k)
-          if (has(w.md, k)) { snprintf(buf, sizeof buf, "tabc[%d]", PROG_FSTRIDE * w.a + 1 + k); ng[k] = buf; }
-        break;
+      case P_LOADF: {  // value + camera partials of frontier value a: 8/16-byte loads of the scalars that are needed
+        bool need[PROG_FSTRIDE] = {true};
+        for (int k = 0; k < 9; ++k) need[1 + k] = grad && has(w.md, k);
+        for (int q = 0; q < PROG_FSTRIDE / 2; ++q)
+          if (need[2 * q] || need[2 * q + 1]) {
+            snprintf(buf, sizeof buf, "    const T2 t%d_ = tab2[%d];\n", q, PROG_FSTRIDE / 2 * w.a + q);
+            s += buf;
+          }
+        auto el = [&](int i) { snprintf(buf, sizeof buf, "t%d_.%c", i / 2, i % 2 ? 'y' : 'x'); return std::string(buf); };
+        nv = el(0);
+        for (int k = 0; k < 9; ++k) if (has(w.md, k)) ng[k] = el(1 + k);
+      } break;
       default:
         break;
     }
@@ -169,7 +175,7 @@ template <typename X> __device__ __forceinline__ X warp_sum_t(X v) {
 // as k_lin_ell (ba_ell.cu) does it for the built-in residual -- r, J -> Jacobian stream, residual array, camera-major
 // copy of the camera part; Hll, g_l and the cost as thread-local sums (fixed vertices and information matrices included).
 extern "C" __global__ void __launch_bounds__(128) prog_fill(const int4 *__restrict__ wdesc, int nW, const int *__restrict__ r_cam,
-    const T2 *__restrict__ r_obs, const T *__restrict__ cam, const T *__restrict__ pt, const T *__restrict__ tab, int tab_stride,
+    const T2 *__restrict__ r_obs, const T *__restrict__ cam16, const T *__restrict__ pt, const T *__restrict__ tab, int tab_stride,
     T2 *__restrict__ WJ, T2 *__restrict__ r_slots, const int *__restrict__ slot_cm, T2 *__restrict__ cm_jr,
     const T *__restrict__ r_info, const unsigned char *__restrict__ cam_fixed, const unsigned char *__restrict__ pt_fixed,
     T *__restrict__ Hll, T *__restrict__ gl, double *__restrict__ partials) {
@@ -190,12 +196,13 @@ extern "C" __global__ void __launch_bounds__(128) prog_fill(const int4 *__restri
     const size_t row = (size_t)row0 + r, slot = row * 32 + lane;
     const int c = r_cam[slot];
     if (c < 0) continue;
-    const T *cp = cam + 9 * (size_t)c;
-    const T in0 = cp[0], in1 = cp[1], in2 = cp[2], in3 = cp[3], in4 = cp[4], in5 = cp[5], in6 = cp[6], in7 = cp[7], in8 = cp[8];
+    const T2 *cp = reinterpret_cast<const T2 *>(cam16 + 16 * (size_t)c);  // 16-scalar aligned rows, the camera in the first 9
+    const T2 c01 = cp[0], c23 = cp[1], c45 = cp[2], c67 = cp[3], c8 = cp[4];
+    const T in0 = c01.x, in1 = c01.y, in2 = c23.x, in3 = c23.y, in4 = c45.x, in5 = c45.y, in6 = c67.x, in7 = c67.y, in8 = c8.x;
     const T2 ob = r_obs[slot];
     const T in12 = ob.x, in13 = ob.y;
-    const T *tabc = tab + (size_t)c * tab_stride;
-    (void)in0; (void)in1; (void)in2; (void)in3; (void)in4; (void)in5; (void)in6; (void)in7; (void)in8; (void)in12; (void)in13; (void)tabc;
+    const T2 *tab2 = reinterpret_cast<const T2 *>(tab + (size_t)c * tab_stride);
+    (void)in0; (void)in1; (void)in2; (void)in3; (void)in4; (void)in5; (void)in6; (void)in7; (void)in8; (void)in12; (void)in13; (void)tab2;
     DECLARE_REGS;
 )";
   s += jit_body(D.obs_code, consts, true, f64);
@@ -267,7 +274,7 @@ extern "C" __global__ void __launch_bounds__(128) prog_fill(const int4 *__restri
   // ---- prog_cost
   s += R"(
 extern "C" __global__ void __launch_bounds__(128) prog_cost(const int4 *__restrict__ wdesc, int nW, const int *__restrict__ r_cam,
-    const T2 *__restrict__ r_obs, const T *__restrict__ cam, const T *__restrict__ dxc, const T *__restrict__ pt,
+    const T2 *__restrict__ r_obs, const T *__restrict__ cam16, const T *__restrict__ pt,
     const T *__restrict__ dxl, const T *__restrict__ tab, int tab_stride, double *__restrict__ partials, int partial_stride) {
   const int lane = threadIdx.x & 31, w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= nW) return;
@@ -285,13 +292,13 @@ extern "C" __global__ void __launch_bounds__(128) prog_cost(const int4 *__restri
     const size_t slot = ((size_t)row0 + r) * 32 + lane;
     const int c = r_cam[slot];
     if (c < 0) continue;
-    const T *cp = cam + 9 * (size_t)c, *dp = dxc + 9 * (size_t)c;
-    const T in0 = cp[0] + dp[0], in1 = cp[1] + dp[1], in2 = cp[2] + dp[2], in3 = cp[3] + dp[3], in4 = cp[4] + dp[4],
-            in5 = cp[5] + dp[5], in6 = cp[6] + dp[6], in7 = cp[7] + dp[7], in8 = cp[8] + dp[8];
+    const T2 *cp = reinterpret_cast<const T2 *>(cam16 + 16 * (size_t)c);  // 16-scalar aligned rows, the camera in the first 9
+    const T2 c01 = cp[0], c23 = cp[1], c45 = cp[2], c67 = cp[3], c8 = cp[4];
+    const T in0 = c01.x, in1 = c01.y, in2 = c23.x, in3 = c23.y, in4 = c45.x, in5 = c45.y, in6 = c67.x, in7 = c67.y, in8 = c8.x;
     const T2 ob = r_obs[slot];
     const T in12 = ob.x, in13 = ob.y;
-    const T *tabc = tab + (size_t)c * tab_stride;
-    (void)in0; (void)in1; (void)in2; (void)in3; (void)in4; (void)in5; (void)in6; (void)in7; (void)in8; (void)in12; (void)in13; (void)tabc;
+    const T2 *tab2 = reinterpret_cast<const T2 *>(tab + (size_t)c * tab_stride);
+    (void)in0; (void)in1; (void)in2; (void)in3; (void)in4; (void)in5; (void)in6; (void)in7; (void)in8; (void)in12; (void)in13; (void)tab2;
     DECLARE_REGS;
 )";
   s += jit_body(D.obs_code, consts, false, f64);

@@ -56,7 +56,7 @@ def test_generated_kernel_source_compiles_for_sm_100a(tmp_path):
         assert 'extern "C" __global__' in src and "prog_fill" in src and "prog_cost" in src
         assert ("typedef double T;" in src) == (dtype == np.float64)
         body = src[src.index("prog_fill"):src.index("prog_cost")]
-        assert "sincos" not in body and "tabc[" in body      # angle-axis -> rotation happens per camera
+        assert "sincos" not in body and "tab2[" in body      # angle-axis -> rotation happens per camera
         assert body.count("// ") < len(prog["code"])          # fewer statements than the caller's program
     bad = prog["code"].copy()
     bad[5, 0] = 99
