@@ -1039,10 +1039,10 @@ struct ImplT : Impl {
     stats.launches += 2;
     return BA_OK;
   }
-  int jit_trial_cost() {
+  int jit_trial_cost(int pstride) {  // partials[w * pstride] = sum of squared trial residuals of warp w
     launch_prog_cam<T>(d, 1, stream);
     if (d.nW > 0) {
-      int nW = d.nW, stride = PROG_FSTRIDE * d.prog_nf, pstride = 2;
+      int nW = d.nW, stride = PROG_FSTRIDE * d.prog_nf;
       // camc2: the trial cameras cam + dx_c, written by k_prog_cam just above
       const void *wdesc = d.wdesc, *r_cam = d.r_cam, *r_obs = d.r_obs, *cam = d.camc2, *pt = d.pt, *dxl = d.dxl, *tab = d.prog_tab2;
       void *partials = d.partials;
@@ -1320,7 +1320,7 @@ struct ImplT : Impl {
     // is  dx^T H dx - 2 g^T dx : the back-substitution pass has Hlp dx_c per point in hand and leaves the point part,
     // a one-block kernel adds the camera part -- ba_eval_trial then only needs the trial cost.
     static const bool model_env = !(getenv("BA_MODEL_QUAD") && atoi(getenv("BA_MODEL_QUAD")) == 0);
-    const bool quad = g.ell && d.store == ST_FACT && !d.r_info && model_env && fuse_norms;
+    const bool quad = g.ell && (d.store == ST_FACT || (d.prog_code && d.prog_jit)) && !d.r_info && model_env && fuse_norms;
     d.model_partials = quad ? model_part : nullptr;
     BA_TRY(schur_edge(SM_BACKSUB, d.xpad, nullptr, 0, false));  // dx_l = w - Hll^-1 Hlp dx_c
     d.model_partials = nullptr;
@@ -1393,12 +1393,18 @@ struct ImplT : Impl {
 
   int eval_trial(double *cost_new, double *model_sq) override {
     BA_CUDA(cudaSetDevice(opt.device));
-    if (g.ell && model_valid && d.store == ST_FACT) {
+    if (g.ell && model_valid && (d.store == ST_FACT || (d.prog_code && d.prog_jit))) {
       // the model term came with the solve (see solve_enqueue); only the trial cost needs the observations
       model_valid = false;
       const double msq = last_cost + h_scal[S_MODEL_PT] + h_scal[S_MODEL_CAM];
-      BA_CUDA(launch_trial_cost_ell<T>(d, stream));
-      stats.launches += 3;
+      if (d.prog_code) {  // user-defined residual: the generated prog_cost kernel, one partial per warp
+        BA_TRY(jit_trial_cost(1));
+        BA_CUDA(launch_reduce_partials<T>(d, 1, S_TRIAL_COST, stream));
+        stats.launches += 1;
+      } else {
+        BA_CUDA(launch_trial_cost_ell<T>(d, stream));
+        stats.launches += 3;
+      }
       BA_TRY(allreduce_scal(S_TRIAL_COST, 1, ncclSum));
       BA_TRY(fetch_scalars());
       if (cost_new) *cost_new = h_scal[S_TRIAL_COST];
@@ -1407,7 +1413,7 @@ struct ImplT : Impl {
     }
     if (g.ell) {
       if (d.store == ST_FACT) BA_TRY(pad_cam(d.dxc));  // the factored trial kernel gathers T_c dx_c
-      if (d.prog_code && d.prog_jit) BA_TRY(jit_trial_cost());
+      if (d.prog_code && d.prog_jit) BA_TRY(jit_trial_cost(2));
       BA_CUDA(launch_trial_ell<T>(d, stream));
     } else {
       BA_CUDA(launch_trial<T>(d, stream));

@@ -1777,6 +1777,13 @@ cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// scal[scal_index .. + ncomp) = per-warp partials summed in warp order (the partials were left by a generated kernel)
+template <typename T>
+cudaError_t launch_reduce_partials(const Dev<T> &d, int ncomp, int scal_index, cudaStream_t st) {
+  k_reduce<0><<<1, 1024, 0, st>>>(d.partials, d.nW, ncomp, d.scal + scal_index);
+  return cudaGetLastError();
+}
+
 // after the back-substitution left the point partials: scal[S_MODEL_PT], scal[S_MODEL_CAM]
 template <typename T>
 cudaError_t launch_model_terms(const Dev<T> &d, cudaStream_t st) {
@@ -1823,6 +1830,7 @@ cudaError_t launch_permute3(const T *src, T *dst, const int *perm, int n, int ga
   template cudaError_t launch_prep_ell<T>(const Dev<T> &, cudaStream_t);                                      \
   template cudaError_t launch_trial_ell<T>(const Dev<T> &, cudaStream_t);                                     \
   template void launch_prog_cam<T>(const Dev<T> &, int, cudaStream_t);                                        \
+  template cudaError_t launch_reduce_partials<T>(const Dev<T> &, int, int, cudaStream_t);                     \
   template cudaError_t launch_trial_cost_ell<T>(const Dev<T> &, cudaStream_t);                                \
   template cudaError_t launch_model_terms<T>(const Dev<T> &, cudaStream_t);                                   \
   template cudaError_t launch_eval_edges_ell<T>(const Dev<T> &, T *, T *, cudaStream_t);                      \

@@ -191,6 +191,7 @@ template <typename T> cudaError_t launch_schur_ell(const Dev<T> &d, int mode, co
 template <typename T> cudaError_t launch_prep_ell(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_trial_ell(const Dev<T> &d, cudaStream_t st);
 template <typename T> void launch_prog_cam(const Dev<T> &d, int trial, cudaStream_t st);
+template <typename T> cudaError_t launch_reduce_partials(const Dev<T> &d, int ncomp, int scal_index, cudaStream_t st);
 template <typename T> cudaError_t launch_trial_cost_ell(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_model_terms(const Dev<T> &d, cudaStream_t st);
 template <typename T> cudaError_t launch_eval_edges_ell(const Dev<T> &d, T *r_slots, T *J_slots, cudaStream_t st);
