@@ -228,6 +228,64 @@ def test_a_residual_that_is_not_bal(tmp_path):
     S.close()
 
 
+def _random_program(seed, n_ops=60):
+    """A random residual: a DAG over all 14 inputs with every op of the instruction set, values kept in a tame range
+    (denominators 2 + cos, square roots of 1 + x^2), camera-only, point-only and mixed subexpressions."""
+    rng = np.random.default_rng(seed)
+    A = _Asm()
+    scale = [1., 1., 1., 1., 1., 1., 1e-3, 1., 1., 1., 1., 1., 1e-2, 1e-2]  # focal length and pixels brought to O(1)
+    pool = [A.sin(A.mul(A.const(scale[k]), A.inp(k))) for k in range(14)]
+    for _ in range(n_ops):
+        op = rng.choice(["add", "sub", "mul", "neg", "sin", "cos", "abs", "sel", "div", "sqrt"])
+        a, b, c, d = (pool[i] for i in rng.integers(0, len(pool), 4))
+        if op in ("add", "sub", "mul"):
+            v = getattr(A, op)(a, b)
+            if op == "mul":
+                v = A.add(v, A.const(float(rng.normal())))
+        elif op in ("neg", "sin", "cos", "abs"):
+            v = getattr(A, op)(a)
+        elif op == "sel":
+            v = A._emit(10, a, b, c, d)
+        elif op == "div":
+            v = A.div(a, A.add(A.const(2.), A.cos(b)))
+        else:
+            v = A.sqrt(A.add(A.const(1.), A.mul(a, a)))
+        pool.append(A.mul(A.const(0.5), v) if op in ("add", "sub") else v)
+    # the two results mix late values with one camera and one point input each, so that every block is populated
+    r0 = A.add(A.add(pool[-1], pool[-3]), A.mul(pool[0], pool[9]))
+    r1 = A.add(A.sub(pool[-2], pool[-4]), A.mul(pool[4], pool[10]))
+    return A.prog(r0, r1)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_programs_against_the_numpy_interpreter(seed):
+    """Fuzz of the whole chain -- validation, camera / observation split, group masks, interpreter (ba_eval_edges) and the
+    generated kernels or the interpreter inside ba_linearize -- on random programs with register reuse."""
+    try:
+        prog = _random_program(seed)
+    except OverflowError:
+        pytest.skip("more than 255 values")
+    if prog["n_slots"] > 48:
+        pytest.skip("needs more registers than the interpreter has")
+    P = make_synthetic(15, 600, 3000, seed=100 + seed)
+    S = _solver(P, prog=prog)
+    r0, J0 = eval_program(prog, edge_inputs(P))
+    assert np.isfinite(J0).all()
+    r, J = S.eval_edges()
+    assert rel_fro(r, r0) <= 1e-12 and rel_fro(J, J0) <= 1e-11
+    cost = S.linearize()
+    assert abs(cost - (r0 ** 2).sum()) <= 1e-11 * cost
+    Hpp = np.zeros((P.nC, 9, 9)); Hll = np.zeros((P.nP, 3, 3)); gc = np.zeros((P.nC, 9)); gl = np.zeros((P.nP, 3))
+    np.add.at(Hpp, P.cam_idx, np.einsum("eri,erj->eij", J0[:, :, :9], J0[:, :, :9]))
+    np.add.at(Hll, P.pt_idx, np.einsum("eri,erj->eij", J0[:, :, 9:], J0[:, :, 9:]))
+    np.add.at(gc, P.cam_idx, -np.einsum("eri,er->ei", J0[:, :, :9], r0))
+    np.add.at(gl, P.pt_idx, -np.einsum("eri,er->ei", J0[:, :, 9:], r0))
+    assert rel_fro(S.read(capi.BUF_HPP), Hpp) <= 1e-10
+    assert rel_fro(S.read(capi.BUF_HLL), Hll) <= 1e-10
+    assert rel_fro(S.read(capi.BUF_G), np.concatenate([gc.ravel(), gl.ravel()])) <= 1e-10
+    S.close()
+
+
 def test_rejects_malformed_programs(tmp_path):
     P = make_synthetic(5, 60, 200, seed=45)
     S = _solver(P)
