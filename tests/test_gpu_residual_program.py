@@ -12,7 +12,7 @@ import pytest
 from megba_b200 import capi
 from megba_b200.synthetic import make_synthetic, read_bal, write_bal
 from oracle.oracle import Oracle
-from residual_program import BIN, build_examples, edge_inputs, eval_program, trace_bal_edge
+from residual_program import BIN, Asm as _Asm, build_examples, edge_inputs, eval_program, random_program as _random_program, trace_bal_edge
 from util import bal_like_problem, rel_fro
 
 pytestmark = pytest.mark.gpu
@@ -133,52 +133,6 @@ def test_program_can_be_cleared_and_fixed_vertices_apply(tmp_path):
     assert rel_fro(camb, cama) <= 1e-7 and rel_fro(ptb, pta) <= 1e-7
 
 
-class _Asm:
-    """A few lines of assembler for residuals written by hand in the tests: values are numbered in order, prog() maps
-    them onto registers that are reused once a value has been read for the last time."""
-
-    def __init__(self):
-        self.code, self.consts = [], []
-
-    def _emit(self, op, a=0, b=0, c=0, d=0):
-        dst = len(self.code)
-        self.code.append([op, dst, a, b, c, d])
-        return dst
-
-    def inp(self, k): return self._emit(0, k)
-    def const(self, x):
-        self.consts.append(float(x))
-        return self._emit(1, len(self.consts) - 1)
-    def add(self, a, b): return self._emit(2, a, b)
-    def sub(self, a, b): return self._emit(3, a, b)
-    def mul(self, a, b): return self._emit(4, a, b)
-    def div(self, a, b): return self._emit(5, a, b)
-    def neg(self, a): return self._emit(6, a)
-    def sqrt(self, a): return self._emit(7, a)
-    def sin(self, a): return self._emit(8, a)
-    def cos(self, a): return self._emit(9, a)
-    def abs(self, a): return self._emit(11, a)
-    def prog(self, o0, o1):
-        nsrc = {0: 0, 1: 0, 6: 1, 7: 1, 8: 1, 9: 1, 10: 4, 11: 1}
-        last = {o0: len(self.code), o1: len(self.code)}
-        for i, (op, dst, *src) in enumerate(self.code):
-            for v in src[:nsrc.get(op, 2)]:
-                last[v] = max(last.get(v, -1), i)
-        reg, free, n, out = {}, [], 0, []
-        for i, (op, dst, *src) in enumerate(self.code):
-            k = nsrc.get(op, 2)
-            ops = [reg[v] for v in src[:k]] + src[k:]
-            for v in set(src[:k]):
-                if last[v] == i:
-                    free.append(reg[v])
-            if free:
-                reg[dst] = free.pop()
-            else:
-                reg[dst], n = n, n + 1
-            out.append([op, reg[dst], *ops])
-        return dict(code=np.array(out, np.uint8), consts=np.array(self.consts), n_slots=n, out=(reg[o0], reg[o1]))
-
-
 def _pinhole_euler_program():
     """A residual that is not the BAL model: Euler rotations about z, x, y by camera[0:3], translation camera[3:6],
     pinhole focal length camera[6] and principal point camera[7:9], with a smooth sqrt-regularised depth."""
@@ -226,35 +180,6 @@ def test_a_residual_that_is_not_bal(tmp_path):
     tr = S.lm_solve(lm_max_iter=15, initial_region=1e3, eps1=1e-12, eps2=1e-14, pcg_max_iter=60, pcg_tol=1e-8)
     assert tr[-1]["cost"] < 1e-6 * tr[0]["cost"]  # Gauss-Newton on a zero-residual problem converges fast
     S.close()
-
-
-def _random_program(seed, n_ops=60):
-    """A random residual: a DAG over all 14 inputs with every op of the instruction set, values kept in a tame range
-    (denominators 2 + cos, square roots of 1 + x^2), camera-only, point-only and mixed subexpressions."""
-    rng = np.random.default_rng(seed)
-    A = _Asm()
-    scale = [1., 1., 1., 1., 1., 1., 1e-3, 1., 1., 1., 1., 1., 1e-2, 1e-2]  # focal length and pixels brought to O(1)
-    pool = [A.sin(A.mul(A.const(scale[k]), A.inp(k))) for k in range(14)]
-    for _ in range(n_ops):
-        op = rng.choice(["add", "sub", "mul", "neg", "sin", "cos", "abs", "sel", "div", "sqrt"])
-        a, b, c, d = (pool[i] for i in rng.integers(0, len(pool), 4))
-        if op in ("add", "sub", "mul"):
-            v = getattr(A, op)(a, b)
-            if op == "mul":
-                v = A.add(v, A.const(float(rng.normal())))
-        elif op in ("neg", "sin", "cos", "abs"):
-            v = getattr(A, op)(a)
-        elif op == "sel":
-            v = A._emit(10, a, b, c, d)
-        elif op == "div":
-            v = A.div(a, A.add(A.const(2.), A.cos(b)))
-        else:
-            v = A.sqrt(A.add(A.const(1.), A.mul(a, a)))
-        pool.append(A.mul(A.const(0.5), v) if op in ("add", "sub") else v)
-    # the two results mix late values with one camera and one point input each, so that every block is populated
-    r0 = A.add(A.add(pool[-1], pool[-3]), A.mul(pool[0], pool[9]))
-    r1 = A.add(A.sub(pool[-2], pool[-4]), A.mul(pool[4], pool[10]))
-    return A.prog(r0, r1)
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
